@@ -1,0 +1,596 @@
+// bsuite_b200 engine: handle management, kernel dispatch, explicit host path and
+// the extern "C" surface declared in include/bsuite_b200.h.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a --fmad=false -lineinfo ...
+// (--fmad=false: CPython/numpy never contract a*b+c; the float-dynamics
+// families must evaluate the reference's expressions operation by operation.)
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/bsuite_b200.h"
+#include "bsb_kernels.cuh"
+
+using namespace bsb;
+
+namespace {
+
+thread_local std::string g_last_error;
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const std::string& msg) { g_last_error = msg; return code; }
+
+#define BSB_CUDA(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t e__ = (expr);                                                            \
+    if (e__ != cudaSuccess)                                                              \
+      return fail(e__ == cudaErrorMemoryAllocation ? BSB_OUT_OF_MEMORY : BSB_CUDA_ERROR, \
+                  std::string(#expr) + ": " + cudaGetErrorString(e__));                  \
+  } while (0)
+
+struct InfoNames { int n; const char* names[BSB_MAX_INFO]; };
+
+InfoNames info_names(int family) {
+  switch (family) {
+    case BSB_DEEP_SEA: return {2, {"total_bad_episodes", "denoised_return", nullptr, nullptr}};
+    case BSB_CATCH: return {1, {"total_regret", nullptr, nullptr, nullptr}};
+    case BSB_CARTPOLE: return {2, {"raw_return", "best_episode", nullptr, nullptr}};
+    case BSB_CARTPOLE_SWINGUP: return {3, {"raw_return", "total_upright", "best_episode", nullptr}};
+    case BSB_MOUNTAIN_CAR: return {1, {"raw_return", nullptr, nullptr, nullptr}};
+    case BSB_MEMORY_CHAIN: return {2, {"total_perfect", "total_regret", nullptr, nullptr}};
+    case BSB_BANDIT: return {1, {"total_regret", nullptr, nullptr, nullptr}};
+    case BSB_UMBRELLA_CHAIN: return {1, {"total_regret", nullptr, nullptr, nullptr}};
+    case BSB_DISCOUNTING_CHAIN: return {0, {nullptr, nullptr, nullptr, nullptr}};
+    case BSB_MNIST: return {1, {"total_regret", nullptr, nullptr, nullptr}};
+  }
+  return {0, {nullptr, nullptr, nullptr, nullptr}};
+}
+
+}  // namespace
+
+struct bsb_env {
+  EnvParams p;
+  int device;             // BSB_DEVICE_HOST or CUDA ordinal
+  int64_t steps_done;
+  InfoNames names;
+  std::vector<void*> allocs;
+  std::vector<std::pair<void*, size_t> > state_blocks;  // snapshot layout
+  // bsb_step_host scratch (device)
+  int32_t* h2d_actions; float* d_reward; double* d_reward64; float* d_discount; int32_t* d_step_type; float* d_obs;
+  cudaStream_t copy_stream;
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev; bool on;
+  explicit DeviceGuard(int dev) : prev(0), on(dev >= 0) { if (on) { cudaGetDevice(&prev); cudaSetDevice(dev); } }
+  ~DeviceGuard() { if (on) cudaSetDevice(prev); }
+};
+
+int env_alloc(bsb_env* e, void** out, size_t bytes, bool snapshot) {
+  if (bytes == 0) { *out = nullptr; return BSB_OK; }
+  void* ptr = nullptr;
+  if (e->device >= 0) {
+    BSB_CUDA(cudaMalloc(&ptr, bytes));
+    BSB_CUDA(cudaMemset(ptr, 0, bytes));
+  } else {
+    ptr = calloc(1, bytes);
+    if (!ptr) return fail(BSB_OUT_OF_MEMORY, "calloc failed");
+  }
+  e->allocs.push_back(ptr);
+  if (snapshot) e->state_blocks.push_back(std::make_pair(ptr, bytes));
+  *out = ptr;
+  return BSB_OK;
+}
+
+int env_upload(bsb_env* e, void* dst, const void* src, size_t bytes) {
+  if (bytes == 0) return BSB_OK;
+  if (e->device >= 0) { BSB_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice)); }
+  else memcpy(dst, src, bytes);
+  return BSB_OK;
+}
+
+template <class T> int env_alloc_t(bsb_env* e, T** out, size_t count, bool snapshot) {
+  void* ptr = nullptr;
+  int rc = env_alloc(e, &ptr, count * sizeof(T), snapshot);
+  *out = static_cast<T*>(ptr);
+  return rc;
+}
+
+// --------------------------- host path --------------------------------------
+template <class F> struct HostEmit {
+  template <class R> static void run(const EnvParams& p, const typename F::Lane& L, R&, float* dst) { F::row(p, L, dst, 1); }
+};
+template <> struct HostEmit<UmbrellaChain> {
+  template <class R> static void run(const EnvParams& p, const UmbrellaChain::Lane& L, R& r, float* dst) { UmbrellaChain::row(p, L, r, dst, 1); }
+};
+template <> struct HostEmit<DeepSea> {
+  template <class R> static void run(const EnvParams& p, const DeepSea::Lane& L, R&, float* dst) {
+    for (int e = 0; e < p.obs_numel; ++e) dst[e] = 0.f;
+    if (L.hot >= 0) dst[L.hot] = 1.f;
+  }
+};
+template <> struct HostEmit<Catch> {
+  template <class R> static void run(const EnvParams& p, const Catch::Lane& L, R&, float* dst) {
+    for (int e = 0; e < p.obs_numel; ++e) dst[e] = 0.f;
+    dst[L.hot_a] = 1.f; dst[L.hot_b] = 1.f;
+  }
+};
+template <> struct HostEmit<Mnist> {
+  template <class R> static void run(const EnvParams& p, const Mnist::Lane& L, R&, float* dst) {
+    if (L.image < 0) { for (int e = 0; e < p.obs_numel; ++e) dst[e] = 0.f; return; }
+    const int8_t* src = p.images + (int64_t)L.image * p.obs_numel;
+    for (int e = 0; e < p.obs_numel; ++e) dst[e] = Mnist::pixel(src[e]);
+  }
+};
+
+template <class F, int RK>
+void host_run(const EnvParams& p, const LaunchArgs& a) {
+  typedef typename RngOf<RK>::type R;
+  const int64_t B = p.batch;
+  const int K = p.obs_numel;
+  const bool noise = p.wrapper == BSB_WRAP_REWARD_NOISE;
+  const bool has_rng = p.rng_pos != nullptr;
+  const bool track = p.ep != nullptr;
+  for (int64_t lane = 0; lane < B; ++lane) {
+    typename F::Lane L;
+    R rng, wrng;
+    EpisodeStats ep;
+    if (a.mode == MODE_INIT) F::init(p, L); else F::load(p, lane, L);
+    if (has_rng) rng_open(rng, p, lane, false);
+    if (noise) rng_open(wrng, p, lane, true);
+    if (track) ep.load(p, lane);
+    if (a.mode == MODE_INIT) {
+      F::ctor_draws(p, L, rng);
+      F::store(p, lane, L);
+      if (has_rng) rng_close(rng, p, lane, false);
+      continue;
+    }
+    for (int64_t t = 0; t < a.T; ++t) {
+      const int64_t off = t * B + lane;
+      int32_t action = 0;
+      if (a.mode == MODE_STEP) {
+        action = a.actions ? a.actions[off]
+                           : sample_action(a.action_seed, p.lane_offset + (uint64_t)lane, (uint64_t)(a.step0 + t), p.num_actions);
+        if (a.actions_out) a.actions_out[off] = action;
+      }
+      const StepOut o = lane_transition<F, R, R>(p, lane, L, rng, wrng, action, a.mode, noise);
+      if (track) ep.track(o);
+      if (a.reward) a.reward[off] = (float)o.reward;
+      if (a.reward_f64) a.reward_f64[off] = o.reward;
+      if (a.discount) a.discount[off] = o.discount;
+      if (a.step_type) a.step_type[off] = o.step_type;
+      HostEmit<F>::run(p, L, rng, a.obs + off * (int64_t)K);
+    }
+    F::store(p, lane, L);
+    if (has_rng) rng_close(rng, p, lane, false);
+    if (noise) rng_close(wrng, p, lane, true);
+    if (track) ep.store(p, lane);
+  }
+}
+
+// --------------------------- device dispatch --------------------------------
+template <class F, int RK, bool kNoise>
+int device_launch(const bsb_env* e, const LaunchArgs& a, cudaStream_t stream) {
+  const int K = e->p.obs_numel;
+  int threads = 128;
+  size_t smem = 0;
+  if (EmitKind<F>::value == EMIT_ROWS) {
+    smem = (size_t)(threads / 32) * 32 * (size_t)K * sizeof(float);
+    while (smem > 96 * 1024 && threads > 32) { threads >>= 1; smem = (size_t)(threads / 32) * 32 * (size_t)K * sizeof(float); }
+    if (smem > 200 * 1024) return fail(BSB_UNSUPPORTED, "observation row too long for the staged emitter");
+    if (smem > 48 * 1024)
+      BSB_CUDA(cudaFuncSetAttribute(transition_kernel<F, RK, kNoise>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  const int64_t B = e->p.batch;
+  const unsigned grid = (unsigned)((B + threads - 1) / threads);
+  transition_kernel<F, RK, kNoise><<<grid, threads, smem, stream>>>(e->p, a);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  BSB_CUDA(cudaGetLastError());
+  return BSB_OK;
+}
+
+template <class F>
+int run_family(bsb_env* e, const LaunchArgs& a, cudaStream_t stream) {
+  const bool mt = e->p.rng_kind == BSB_RNG_MT19937;
+  if (e->device < 0) {
+    if (mt) host_run<F, 1>(e->p, a); else host_run<F, 0>(e->p, a);
+    return BSB_OK;
+  }
+  const bool noise = e->p.wrapper == BSB_WRAP_REWARD_NOISE && a.mode != MODE_INIT;
+  if (mt) return noise ? device_launch<F, 1, true>(e, a, stream) : device_launch<F, 1, false>(e, a, stream);
+  return noise ? device_launch<F, 0, true>(e, a, stream) : device_launch<F, 0, false>(e, a, stream);
+}
+
+int run(bsb_env* e, const LaunchArgs& a, cudaStream_t stream) {
+  DeviceGuard guard(e->device);
+  switch (e->p.family) {
+    case BSB_DEEP_SEA: return run_family<DeepSea>(e, a, stream);
+    case BSB_CATCH: return run_family<Catch>(e, a, stream);
+    case BSB_CARTPOLE: return run_family<Cartpole>(e, a, stream);
+    case BSB_CARTPOLE_SWINGUP: return run_family<CartpoleSwingup>(e, a, stream);
+    case BSB_MOUNTAIN_CAR: return run_family<MountainCar>(e, a, stream);
+    case BSB_MEMORY_CHAIN: return run_family<MemoryChain>(e, a, stream);
+    case BSB_BANDIT: return run_family<Bandit>(e, a, stream);
+    case BSB_UMBRELLA_CHAIN: return run_family<UmbrellaChain>(e, a, stream);
+    case BSB_DISCOUNTING_CHAIN: return run_family<DiscountingChain>(e, a, stream);
+    case BSB_MNIST: return run_family<Mnist>(e, a, stream);
+  }
+  return fail(BSB_INVALID_ARGUMENT, "unknown family");
+}
+
+LaunchArgs make_args(const bsb_env* e, const bsb_outputs* out, const int32_t* actions, int64_t T, int mode) {
+  LaunchArgs a;
+  memset(&a, 0, sizeof(a));
+  a.actions = actions;
+  if (out) { a.obs = out->observation; a.reward = out->reward; a.reward_f64 = out->reward_f64; a.discount = out->discount; a.step_type = out->step_type; }
+  a.T = T; a.step0 = e->steps_done; a.mode = mode;
+  const size_t step_bytes = (size_t)e->p.batch * (size_t)e->p.obs_numel * sizeof(float);
+  a.obs_vec_ok = (out && (reinterpret_cast<uintptr_t>(out->observation) % 16 == 0) && (T == 1 || step_bytes % 16 == 0)) ? 1 : 0;
+  return a;
+}
+
+int validate(const bsb_config& c, int64_t batch, int* obs_rows, int* obs_cols, int* n_actions) {
+  if (batch <= 0) return fail(BSB_INVALID_ARGUMENT, "batch must be positive");
+  if (c.wrapper < 0 || c.wrapper > 2) return fail(BSB_INVALID_ARGUMENT, "unknown wrapper");
+  if (c.rng_kind < 0 || c.rng_kind > 1) return fail(BSB_INVALID_ARGUMENT, "unknown rng_kind");
+  switch (c.family) {
+    case BSB_DEEP_SEA:
+      if (c.size < 1 || c.size > 255) return fail(BSB_INVALID_ARGUMENT, "deep_sea size must be in [1, 255]");
+      if (!c.table || c.table_bytes != (int64_t)c.size * c.size) return fail(BSB_INVALID_ARGUMENT, "deep_sea needs a uint8 [N*N] action mapping table");
+      *obs_rows = c.size; *obs_cols = c.size; *n_actions = 2; break;
+    case BSB_CATCH:
+      if (c.rows < 2 || c.rows > 255 || c.columns < 1 || c.columns > 255) return fail(BSB_INVALID_ARGUMENT, "catch rows in [2,255], columns in [1,255]");
+      *obs_rows = c.rows; *obs_cols = c.columns; *n_actions = 3; break;
+    case BSB_CARTPOLE: *obs_rows = 1; *obs_cols = 6; *n_actions = 3; break;
+    case BSB_CARTPOLE_SWINGUP: *obs_rows = 1; *obs_cols = 8; *n_actions = 3; break;
+    case BSB_MOUNTAIN_CAR:
+      if (c.max_steps < 1) return fail(BSB_INVALID_ARGUMENT, "mountain_car max_steps must be >= 1");
+      *obs_rows = 1; *obs_cols = 3; *n_actions = 3; break;
+    case BSB_MEMORY_CHAIN:
+      if (c.num_bits < 1 || c.num_bits > 64) return fail(BSB_UNSUPPORTED, "memory_chain num_bits must be in [1, 64]");
+      if (c.memory_length < 1 || c.memory_length >= (1 << 24)) return fail(BSB_INVALID_ARGUMENT, "memory_length must be in [1, 2^24)");
+      *obs_rows = 1; *obs_cols = c.num_bits + 2; *n_actions = 2; break;
+    case BSB_BANDIT:
+      if (c.num_actions < 1) return fail(BSB_INVALID_ARGUMENT, "bandit num_actions must be >= 1");
+      if (!c.table || c.table_bytes != (int64_t)c.num_actions * 8) return fail(BSB_INVALID_ARGUMENT, "bandit needs a float64 [num_actions] reward table");
+      *obs_rows = 1; *obs_cols = 1; *n_actions = c.num_actions; break;
+    case BSB_UMBRELLA_CHAIN:
+      if (c.chain_length < 1 || c.chain_length >= (1 << 24)) return fail(BSB_INVALID_ARGUMENT, "chain_length must be in [1, 2^24)");
+      if (c.n_distractor < 0 || c.n_distractor > 1533) return fail(BSB_UNSUPPORTED, "n_distractor must be in [0, 1533]");
+      *obs_rows = 1; *obs_cols = 3 + c.n_distractor; *n_actions = 2; break;
+    case BSB_DISCOUNTING_CHAIN:
+      if (!c.table || c.table_bytes != 5 * 8) return fail(BSB_INVALID_ARGUMENT, "discounting_chain needs a float64 [5] reward table");
+      *obs_rows = 1; *obs_cols = 2; *n_actions = 5; break;
+    case BSB_MNIST:
+      if (c.num_data < 1 || c.image_rows < 1 || c.image_cols < 1) return fail(BSB_INVALID_ARGUMENT, "mnist needs num_data, image_rows, image_cols");
+      if (!c.table || c.table_bytes != (int64_t)c.num_data * c.image_rows * c.image_cols) return fail(BSB_INVALID_ARGUMENT, "mnist needs an int8 image table");
+      if (!c.table2 || c.table2_bytes != c.num_data) return fail(BSB_INVALID_ARGUMENT, "mnist needs a uint8 label table");
+      *obs_rows = c.image_rows; *obs_cols = c.image_cols; *n_actions = 10; break;
+    default: return fail(BSB_INVALID_ARGUMENT, "unknown family");
+  }
+  return BSB_OK;
+}
+
+bool family_uses_env_rng(const bsb_config& c) {
+  switch (c.family) {
+    case BSB_DEEP_SEA: return !c.deterministic;
+    case BSB_BANDIT: case BSB_DISCOUNTING_CHAIN: return false;
+    default: return true;
+  }
+}
+bool family_uses_env_gauss(const bsb_config& c) { return c.family == BSB_DEEP_SEA && !c.deterministic; }
+
+void destroy_env(bsb_env* e) {
+  DeviceGuard guard(e->device);
+  for (size_t k = 0; k < e->allocs.size(); ++k) { if (e->device >= 0) cudaFree(e->allocs[k]); else free(e->allocs[k]); }
+  if (e->device >= 0) {
+    if (e->h2d_actions) cudaFree(e->h2d_actions);
+    if (e->d_reward) cudaFree(e->d_reward);
+    if (e->d_reward64) cudaFree(e->d_reward64);
+    if (e->d_discount) cudaFree(e->d_discount);
+    if (e->d_step_type) cudaFree(e->d_step_type);
+    if (e->d_obs) cudaFree(e->d_obs);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+  }
+  delete e;
+}
+
+}  // namespace
+
+// ============================ extern "C" ====================================
+extern "C" {
+
+int32_t bsb_abi_version(void) { return BSB_ABI_VERSION; }
+const char* bsb_last_error(void) { return g_last_error.c_str(); }
+int64_t bsb_launch_count(void) { return g_launches.load(); }
+
+int32_t bsb_create(const bsb_config* config, int64_t batch, int32_t device, uint64_t seed, uint64_t lane_offset, bsb_env** out) {
+  if (!config || !out) return fail(BSB_INVALID_ARGUMENT, "null argument");
+  *out = nullptr;
+  const bsb_config& c = *config;
+  int obs_rows = 0, obs_cols = 0, n_actions = 0;
+  int rc = validate(c, batch, &obs_rows, &obs_cols, &n_actions);
+  if (rc != BSB_OK) return rc;
+  if (device >= 0) {
+    int count = 0;
+    cudaError_t err = cudaGetDeviceCount(&count);
+    if (err != cudaSuccess || count <= 0)
+      return fail(BSB_CUDA_ERROR, std::string("no CUDA device available (") + cudaGetErrorString(err) +
+                                      "); this engine has no implicit CPU fallback -- pass device=BSB_DEVICE_HOST explicitly for the host path");
+    if (device >= count) return fail(BSB_INVALID_ARGUMENT, "device ordinal out of range");
+  } else if (device != BSB_DEVICE_HOST) {
+    return fail(BSB_INVALID_ARGUMENT, "device must be >= 0 or BSB_DEVICE_HOST");
+  }
+
+  bsb_env* e = new bsb_env();
+  memset(&e->p, 0, sizeof(e->p));
+  e->device = device; e->steps_done = 0; e->names = info_names(c.family);
+  e->h2d_actions = nullptr; e->d_reward = nullptr; e->d_reward64 = nullptr; e->d_discount = nullptr; e->d_step_type = nullptr; e->d_obs = nullptr;
+  e->copy_stream = nullptr;
+  DeviceGuard guard(device);
+
+  EnvParams& p = e->p;
+  p.family = c.family; p.wrapper = c.wrapper; p.rng_kind = c.rng_kind; p.flags = c.flags;
+  p.size = c.size; p.deterministic = c.deterministic; p.rows = c.rows; p.columns = c.columns;
+  p.memory_length = c.memory_length; p.num_bits = c.num_bits; p.chain_length = c.chain_length; p.n_distractor = c.n_distractor;
+  p.num_actions = n_actions; p.max_steps = c.max_steps; p.num_data = c.num_data; p.image_numel = c.image_rows * c.image_cols;
+  p.obs_rows = obs_rows; p.obs_cols = obs_cols; p.obs_numel = obs_rows * obs_cols; p.n_info = e->names.n;
+  p.batch = batch; p.seed = seed; p.lane_offset = lane_offset;
+  if (c.family == BSB_DEEP_SEA) { p.move_cost_step = c.unscaled_move_cost / (double)c.size; p.inv_size = 1.0 / (double)c.size; }
+  p.height_threshold = c.height_threshold; p.x_threshold = c.x_threshold; p.timescale = c.timescale; p.max_time = c.max_time;
+  p.init_range = c.init_range; p.theta_dot_threshold = c.theta_dot_threshold; p.x_reward_threshold = c.x_reward_threshold;
+  p.move_cost = c.move_cost; p.noise_scale = c.noise_scale; p.reward_scale = c.reward_scale;
+  {  // cartpole.py:106-112 and the locals of step_cartpole (:40-47)
+    const double mass_cart = 1.0, mass_pole = 0.1, length = 0.5;
+    p.cp_force_mag = 10.0; p.cp_gravity = 9.8; p.cp_length = length; p.cp_mass_pole = mass_pole;
+    p.cp_pl = mass_pole * length; p.cp_mass_total = mass_cart + mass_pole;
+    p.cp_four_thirds = 4.0 / 3.0; p.cp_two_pi = 2.0 * 3.141592653589793;
+  }
+
+#define BSB_TRY(expr) do { rc = (expr); if (rc != BSB_OK) { destroy_env(e); return rc; } } while (0)
+  const size_t B = (size_t)batch;
+  // tables
+  if (c.family == BSB_DEEP_SEA) {
+    const int cells = c.size * c.size;
+    std::vector<uint32_t> bits((size_t)(cells + 31) / 32, 0u);
+    const uint8_t* m = static_cast<const uint8_t*>(c.table);
+    for (int k = 0; k < cells; ++k) if (m[k]) bits[(size_t)k >> 5] |= 1u << (k & 31);
+    uint32_t* d = nullptr;
+    BSB_TRY(env_alloc_t(e, &d, bits.size(), false));
+    BSB_TRY(env_upload(e, d, bits.data(), bits.size() * 4));
+    p.mapping_bits = d;
+  } else if (c.family == BSB_BANDIT || c.family == BSB_DISCOUNTING_CHAIN) {
+    double* d = nullptr;
+    BSB_TRY(env_alloc_t(e, &d, (size_t)c.table_bytes / 8, false));
+    BSB_TRY(env_upload(e, d, c.table, (size_t)c.table_bytes));
+    p.reward_table = d;
+  } else if (c.family == BSB_MNIST) {
+    int8_t* d = nullptr; uint8_t* l = nullptr;
+    BSB_TRY(env_alloc_t(e, &d, (size_t)c.table_bytes, false));
+    BSB_TRY(env_upload(e, d, c.table, (size_t)c.table_bytes));
+    BSB_TRY(env_alloc_t(e, &l, (size_t)c.table2_bytes, false));
+    BSB_TRY(env_upload(e, l, c.table2, (size_t)c.table2_bytes));
+    p.images = d; p.labels = l;
+  }
+  // lane state
+  BSB_TRY(env_alloc_t(e, &p.st_word, B, true));
+  if (c.family == BSB_MEMORY_CHAIN) BSB_TRY(env_alloc_t(e, &p.st_ctx, B, true));
+  if (c.family == BSB_CARTPOLE || c.family == BSB_CARTPOLE_SWINGUP) BSB_TRY(env_alloc_t(e, &p.st_f64, 6 * B, true));
+  if (c.family == BSB_MOUNTAIN_CAR) BSB_TRY(env_alloc_t(e, &p.st_f64, 2 * B, true));
+  BSB_TRY(env_alloc_t(e, &p.info, (size_t)BSB_MAX_INFO * B, true));
+  if (c.flags & BSB_FLAG_TRACK_EPISODES) BSB_TRY(env_alloc_t(e, &p.ep, 7 * B, true));
+  // RNG state
+  const bool env_rng = family_uses_env_rng(c);
+  const bool noise = c.wrapper == BSB_WRAP_REWARD_NOISE;
+  if (env_rng) {
+    BSB_TRY(env_alloc_t(e, &p.rng_pos, B, true));
+    if (family_uses_env_gauss(c)) BSB_TRY(env_alloc_t(e, &p.rng_gauss, B, true));
+  }
+  if (noise) {
+    BSB_TRY(env_alloc_t(e, &p.wrng_pos, B, true));
+    BSB_TRY(env_alloc_t(e, &p.wrng_gauss, B, true));
+  }
+  if (c.rng_kind == BSB_RNG_MT19937 && (env_rng || noise)) {
+    // numpy.random.RandomState(seed + global lane); the wrapper's RandomState is
+    // seeded with the SAME integer as the environment's (wrappers.py:267).
+    std::vector<uint32_t> keys(624 * B);
+    std::vector<int32_t> idx(B, 624);
+    for (size_t i = 0; i < B; ++i) mt19937_seed_host(keys.data() + i, (int64_t)B, (uint32_t)(seed + lane_offset + i));
+    if (env_rng) {
+      BSB_TRY(env_alloc_t(e, &p.mt_key, 624 * B, true)); BSB_TRY(env_upload(e, p.mt_key, keys.data(), keys.size() * 4));
+      BSB_TRY(env_alloc_t(e, &p.mt_idx, B, true)); BSB_TRY(env_upload(e, p.mt_idx, idx.data(), B * 4));
+    }
+    if (noise) {
+      BSB_TRY(env_alloc_t(e, &p.wmt_key, 624 * B, true)); BSB_TRY(env_upload(e, p.wmt_key, keys.data(), keys.size() * 4));
+      BSB_TRY(env_alloc_t(e, &p.wmt_idx, B, true)); BSB_TRY(env_upload(e, p.wmt_idx, idx.data(), B * 4));
+    }
+  }
+  // constructor: _reset_next_step = True and the constructor's RNG draws
+  LaunchArgs a = make_args(e, nullptr, nullptr, 0, MODE_INIT);
+  BSB_TRY(run(e, a, nullptr));
+  if (device >= 0) {
+    cudaError_t err = cudaDeviceSynchronize();
+    if (err != cudaSuccess) { destroy_env(e); return fail(BSB_CUDA_ERROR, std::string("init kernel: ") + cudaGetErrorString(err)); }
+  }
+#undef BSB_TRY
+  *out = e;
+  return BSB_OK;
+}
+
+int32_t bsb_destroy(bsb_env* env) { if (env) destroy_env(env); return BSB_OK; }
+
+int32_t bsb_obs_numel(const bsb_env* env, int64_t* numel) {
+  if (!env || !numel) return fail(BSB_INVALID_ARGUMENT, "null argument");
+  *numel = env->p.obs_numel; return BSB_OK;
+}
+int32_t bsb_obs_shape(const bsb_env* env, int32_t* rows, int32_t* cols) {
+  if (!env || !rows || !cols) return fail(BSB_INVALID_ARGUMENT, "null argument");
+  *rows = env->p.obs_rows; *cols = env->p.obs_cols; return BSB_OK;
+}
+int32_t bsb_num_actions(const bsb_env* env, int32_t* n) {
+  if (!env || !n) return fail(BSB_INVALID_ARGUMENT, "null argument");
+  *n = env->p.num_actions; return BSB_OK;
+}
+int32_t bsb_batch(const bsb_env* env, int64_t* batch) {
+  if (!env || !batch) return fail(BSB_INVALID_ARGUMENT, "null argument");
+  *batch = env->p.batch; return BSB_OK;
+}
+int32_t bsb_steps_done(const bsb_env* env, int64_t* steps) {
+  if (!env || !steps) return fail(BSB_INVALID_ARGUMENT, "null argument");
+  *steps = env->steps_done; return BSB_OK;
+}
+
+int32_t bsb_reset(bsb_env* env, const bsb_outputs* out, void* stream) {
+  if (!env || !out || !out->observation) return fail(BSB_INVALID_ARGUMENT, "bsb_reset needs outputs with an observation buffer");
+  LaunchArgs a = make_args(env, out, nullptr, 1, MODE_RESET);
+  int rc = run(env, a, static_cast<cudaStream_t>(stream));
+  if (rc == BSB_OK) env->steps_done += 1;
+  return rc;
+}
+
+int32_t bsb_step(bsb_env* env, const int32_t* actions, const bsb_outputs* out, void* stream) {
+  if (!env || !actions || !out || !out->observation) return fail(BSB_INVALID_ARGUMENT, "bsb_step needs actions and outputs with an observation buffer");
+  LaunchArgs a = make_args(env, out, actions, 1, MODE_STEP);
+  int rc = run(env, a, static_cast<cudaStream_t>(stream));
+  if (rc == BSB_OK) env->steps_done += 1;
+  return rc;
+}
+
+int32_t bsb_rollout(bsb_env* env, int64_t num_steps, const int32_t* actions, uint64_t action_seed,
+                    const bsb_outputs* out, int32_t* actions_out, void* stream) {
+  if (!env || !out || !out->observation) return fail(BSB_INVALID_ARGUMENT, "bsb_rollout needs outputs with an observation buffer");
+  if (num_steps <= 0) return fail(BSB_INVALID_ARGUMENT, "num_steps must be positive");
+  LaunchArgs a = make_args(env, out, actions, num_steps, MODE_STEP);
+  a.action_seed = action_seed; a.actions_out = actions_out;
+  int rc = run(env, a, static_cast<cudaStream_t>(stream));
+  if (rc == BSB_OK) env->steps_done += num_steps;
+  return rc;
+}
+
+int32_t bsb_random_actions(uint64_t action_seed, uint64_t lane_offset, int64_t batch, int64_t first_step,
+                           int64_t num_steps, int32_t num_actions, int32_t* out) {
+  if (!out || batch <= 0 || num_steps <= 0 || num_actions <= 0) return fail(BSB_INVALID_ARGUMENT, "bad arguments");
+  for (int64_t t = 0; t < num_steps; ++t)
+    for (int64_t i = 0; i < batch; ++i)
+      out[t * batch + i] = sample_action(action_seed, lane_offset + (uint64_t)i, (uint64_t)(first_step + t), num_actions);
+  return BSB_OK;
+}
+
+int32_t bsb_info_count(const bsb_env* env, int32_t* count) {
+  if (!env || !count) return fail(BSB_INVALID_ARGUMENT, "null argument");
+  *count = env->names.n; return BSB_OK;
+}
+const char* bsb_info_name(const bsb_env* env, int32_t index) {
+  if (!env || index < 0 || index >= env->names.n) return nullptr;
+  return env->names.names[index];
+}
+
+static int copy_field(bsb_env* env, const double* src, double* dst, void* stream) {
+  const size_t bytes = (size_t)env->p.batch * sizeof(double);
+  if (env->device >= 0) {
+    DeviceGuard guard(env->device);
+    BSB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+  } else {
+    memcpy(dst, src, bytes);
+  }
+  return BSB_OK;
+}
+
+int32_t bsb_read_info(bsb_env* env, int32_t index, double* dst, void* stream) {
+  if (!env || !dst) return fail(BSB_INVALID_ARGUMENT, "null argument");
+  if (index < 0 || index >= env->names.n) return fail(BSB_INVALID_ARGUMENT, "info index out of range");
+  return copy_field(env, env->p.info + (size_t)index * (size_t)env->p.batch, dst, stream);
+}
+
+int32_t bsb_read_episode_stats(bsb_env* env, int32_t field, double* dst, void* stream) {
+  if (!env || !dst) return fail(BSB_INVALID_ARGUMENT, "null argument");
+  if (!env->p.ep) return fail(BSB_INVALID_ARGUMENT, "environment was created without BSB_FLAG_TRACK_EPISODES");
+  if (field < 0 || field >= 7) return fail(BSB_INVALID_ARGUMENT, "episode-stat field out of range");
+  return copy_field(env, env->p.ep + (size_t)field * (size_t)env->p.batch, dst, stream);
+}
+
+int32_t bsb_state_bytes(const bsb_env* env, int64_t* nbytes) {
+  if (!env || !nbytes) return fail(BSB_INVALID_ARGUMENT, "null argument");
+  size_t total = sizeof(int64_t);
+  for (size_t k = 0; k < env->state_blocks.size(); ++k) total += env->state_blocks[k].second;
+  *nbytes = (int64_t)total; return BSB_OK;
+}
+
+int32_t bsb_get_state(bsb_env* env, void* dst_host, int64_t nbytes, void* stream) {
+  int64_t need = 0;
+  if (!env || !dst_host) return fail(BSB_INVALID_ARGUMENT, "null argument");
+  bsb_state_bytes(env, &need);
+  if (nbytes != need) return fail(BSB_INVALID_ARGUMENT, "state buffer has the wrong size");
+  DeviceGuard guard(env->device);
+  char* dst = static_cast<char*>(dst_host);
+  memcpy(dst, &env->steps_done, sizeof(int64_t)); dst += sizeof(int64_t);
+  if (env->device >= 0) BSB_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  for (size_t k = 0; k < env->state_blocks.size(); ++k) {
+    if (env->device >= 0) BSB_CUDA(cudaMemcpy(dst, env->state_blocks[k].first, env->state_blocks[k].second, cudaMemcpyDeviceToHost));
+    else memcpy(dst, env->state_blocks[k].first, env->state_blocks[k].second);
+    dst += env->state_blocks[k].second;
+  }
+  return BSB_OK;
+}
+
+int32_t bsb_set_state(bsb_env* env, const void* src_host, int64_t nbytes, void* stream) {
+  int64_t need = 0;
+  if (!env || !src_host) return fail(BSB_INVALID_ARGUMENT, "null argument");
+  bsb_state_bytes(env, &need);
+  if (nbytes != need) return fail(BSB_INVALID_ARGUMENT, "state buffer has the wrong size");
+  DeviceGuard guard(env->device);
+  const char* src = static_cast<const char*>(src_host);
+  memcpy(&env->steps_done, src, sizeof(int64_t)); src += sizeof(int64_t);
+  if (env->device >= 0) BSB_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  for (size_t k = 0; k < env->state_blocks.size(); ++k) {
+    if (env->device >= 0) BSB_CUDA(cudaMemcpy(env->state_blocks[k].first, src, env->state_blocks[k].second, cudaMemcpyHostToDevice));
+    else memcpy(env->state_blocks[k].first, src, env->state_blocks[k].second);
+    src += env->state_blocks[k].second;
+  }
+  return BSB_OK;
+}
+
+int32_t bsb_step_host(bsb_env* env, const int32_t* actions, const bsb_outputs* host_out, float* device_obs) {
+  if (!env || !actions || !host_out) return fail(BSB_INVALID_ARGUMENT, "null argument");
+  if (env->device < 0) {
+    if (!host_out->observation) return fail(BSB_INVALID_ARGUMENT, "a host environment writes observations to host_out->observation");
+    return bsb_step(env, actions, host_out, nullptr);
+  }
+  if (!host_out->observation && !device_obs) return fail(BSB_INVALID_ARGUMENT, "need host_out->observation or device_obs");
+  DeviceGuard guard(env->device);
+  const size_t B = (size_t)env->p.batch, K = (size_t)env->p.obs_numel;
+  if (!env->copy_stream) BSB_CUDA(cudaStreamCreateWithFlags(&env->copy_stream, cudaStreamNonBlocking));
+  if (!env->h2d_actions) BSB_CUDA(cudaMalloc(&env->h2d_actions, B * 4));
+  if (host_out->reward && !env->d_reward) BSB_CUDA(cudaMalloc(&env->d_reward, B * 4));
+  if (host_out->reward_f64 && !env->d_reward64) BSB_CUDA(cudaMalloc(&env->d_reward64, B * 8));
+  if (host_out->discount && !env->d_discount) BSB_CUDA(cudaMalloc(&env->d_discount, B * 4));
+  if (host_out->step_type && !env->d_step_type) BSB_CUDA(cudaMalloc(&env->d_step_type, B * 4));
+  if (!device_obs && !env->d_obs) BSB_CUDA(cudaMalloc(&env->d_obs, B * K * 4));
+  cudaStream_t s = env->copy_stream;
+  BSB_CUDA(cudaMemcpyAsync(env->h2d_actions, actions, B * 4, cudaMemcpyHostToDevice, s));
+  bsb_outputs dev;
+  dev.observation = device_obs ? device_obs : env->d_obs;
+  dev.reward = host_out->reward ? env->d_reward : nullptr;
+  dev.reward_f64 = host_out->reward_f64 ? env->d_reward64 : nullptr;
+  dev.discount = host_out->discount ? env->d_discount : nullptr;
+  dev.step_type = host_out->step_type ? env->d_step_type : nullptr;
+  int rc = bsb_step(env, env->h2d_actions, &dev, s);
+  if (rc != BSB_OK) return rc;
+  if (host_out->reward) BSB_CUDA(cudaMemcpyAsync(host_out->reward, dev.reward, B * 4, cudaMemcpyDeviceToHost, s));
+  if (host_out->reward_f64) BSB_CUDA(cudaMemcpyAsync(host_out->reward_f64, dev.reward_f64, B * 8, cudaMemcpyDeviceToHost, s));
+  if (host_out->discount) BSB_CUDA(cudaMemcpyAsync(host_out->discount, dev.discount, B * 4, cudaMemcpyDeviceToHost, s));
+  if (host_out->step_type) BSB_CUDA(cudaMemcpyAsync(host_out->step_type, dev.step_type, B * 4, cudaMemcpyDeviceToHost, s));
+  if (host_out->observation) BSB_CUDA(cudaMemcpyAsync(host_out->observation, dev.observation, B * K * 4, cudaMemcpyDeviceToHost, s));
+  BSB_CUDA(cudaStreamSynchronize(s));
+  return BSB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,410 @@
+"""Python faces of the engine.
+
+`BatchedEnvironment`  -- B lanes of one bsuite environment stepping in lock-step;
+    `reset()/step(actions)` return a `dm_env.TimeStep` whose fields are torch
+    tensors living on the environment's device (agents consume observations on
+    the GPU directly).  FIRST lanes carry reward = 0 / discount = 0 and are
+    identified by `step_type == 0` (the reference returns `None` there).
+`DmEnvAdapter`        -- a B = 1 `dm_env.Environment` with numpy observations,
+    Python-float rewards and `None` on FIRST: the object contract of
+    `bsuite/environments/base.py:34-77`, for unmodified agents.
+
+Both call the C ABI (include/bsuite_b200.h) through ctypes; torch is used only
+to allocate device memory and to pick the CUDA stream.
+"""
+
+import ctypes
+from typing import Any, Dict, Optional, Sequence, Union
+
+import numpy as np
+
+from bsuite_b200 import _lib
+from bsuite_b200 import dm_env
+from bsuite_b200.experiments import EnvSpec
+
+specs = dm_env.specs
+
+_INT_INFO = frozenset(['total_bad_episodes', 'total_perfect'])
+_MASK64 = (1 << 64) - 1
+
+
+def _fresh_seed() -> int:
+  """seed=None in the reference means OS entropy (numpy RandomState(None))."""
+  return int(np.random.SeedSequence().generate_state(1, dtype=np.uint32)[0])
+
+
+def _resolve_device(device) -> int:
+  """Returns a CUDA ordinal or DEVICE_HOST; never silently falls back."""
+  import torch
+  if device is None:
+    device = 'cuda'
+  dev = torch.device(device)
+  if dev.type == 'cpu':
+    return _lib.DEVICE_HOST
+  if dev.type != 'cuda':
+    raise ValueError(f'unsupported device {device!r}: expected "cuda[:i]" or "cpu"')
+  if not torch.cuda.is_available():
+    raise RuntimeError(
+        'bsuite_b200: a CUDA device was requested but none is available. There is no implicit CPU '
+        'fallback; pass device="cpu" explicitly to use the host path of the C ABI.')
+  return dev.index if dev.index is not None else torch.cuda.current_device()
+
+
+def _make_config(spec: EnvSpec, rng_kind: int, flags: int):
+  cfg = _lib.Config()
+  cfg.family = spec.family
+  cfg.wrapper = spec.wrapper
+  cfg.rng_kind = rng_kind
+  cfg.flags = flags
+  cfg.deterministic = 1
+  cfg.reward_scale = 1.0
+  for key, value in spec.fields.items():
+    setattr(cfg, key, value)
+  keep = []
+  if spec.table is not None:
+    table = np.ascontiguousarray(spec.table)
+    cfg.table = table.ctypes.data
+    cfg.table_bytes = table.nbytes
+    keep.append(table)
+  if spec.table2 is not None:
+    table2 = np.ascontiguousarray(spec.table2)
+    cfg.table2 = table2.ctypes.data
+    cfg.table2_bytes = table2.nbytes
+    keep.append(table2)
+  return cfg, keep
+
+
+class _Handle:
+  """Owns one bsb_env*."""
+
+  def __init__(self, spec: EnvSpec, batch: int, device_ordinal: int, seed: int, lane_offset: int,
+               rng_kind: int, flags: int):
+    self.lib = _lib.load()
+    cfg, keep = _make_config(spec, rng_kind, flags)
+    ptr = ctypes.c_void_p()
+    _lib.check(self.lib.bsb_create(ctypes.byref(cfg), batch, device_ordinal, seed & _MASK64,
+                                   lane_offset & _MASK64, ctypes.byref(ptr)))
+    del keep
+    self.ptr = ptr
+
+  def close(self):
+    if self.ptr is not None and self.ptr.value:
+      self.lib.bsb_destroy(self.ptr)
+      self.ptr = None
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:  # interpreter shutdown
+      pass
+
+
+class StepBuffers:
+  """Caller-owned output tensors for one step (or T fused steps)."""
+
+  def __init__(self, observation, reward, discount, step_type, actions=None):
+    self.observation = observation
+    self.reward = reward
+    self.discount = discount
+    self.step_type = step_type
+    self.actions = actions
+
+  def as_outputs(self) -> _lib.Outputs:
+    import torch
+    out = _lib.Outputs()
+    out.observation = self.observation.data_ptr()
+    if self.reward is not None:
+      if self.reward.dtype == torch.float64:
+        out.reward_f64 = self.reward.data_ptr()
+      else:
+        out.reward = self.reward.data_ptr()
+    if self.discount is not None:
+      out.discount = self.discount.data_ptr()
+    if self.step_type is not None:
+      out.step_type = self.step_type.data_ptr()
+    return out
+
+  def timestep(self) -> 'dm_env.TimeStep':
+    return dm_env.TimeStep(step_type=self.step_type, reward=self.reward, discount=self.discount,
+                           observation=self.observation)
+
+
+class BatchedEnvironment:
+  """`batch` independent lanes of one environment on one device."""
+
+  def __init__(self, spec: EnvSpec, batch: int, device='cuda', seed: Optional[int] = None,
+               rng: str = 'philox', lane_offset: int = 0, track_episodes: bool = False,
+               reward_dtype='float32'):
+    import torch
+    self._torch = torch
+    self._spec = spec
+    self._batch = int(batch)
+    self._ordinal = _resolve_device(device)
+    self._device = torch.device('cpu') if self._ordinal < 0 else torch.device('cuda', self._ordinal)
+    if rng not in ('philox', 'mt19937'):
+      raise ValueError(f'rng must be "philox" or "mt19937", got {rng!r}')
+    self._rng_kind = _lib.RNG_PHILOX if rng == 'philox' else _lib.RNG_MT19937
+    seed = spec.seed if spec.seed is not None else seed
+    self._seed = _fresh_seed() if seed is None else int(seed)
+    if self._rng_kind == _lib.RNG_MT19937 and not 0 <= self._seed < 2**32:
+      raise ValueError('Seed must be between 0 and 2**32 - 1')   # numpy's own message
+    self._lane_offset = int(lane_offset)
+    flags = _lib.FLAG_TRACK_EPISODES if track_episodes else 0
+    self._track = bool(track_episodes)
+    self._reward_dtype = torch.float64 if str(reward_dtype).endswith('64') else torch.float32
+    self._handle = _Handle(spec, self._batch, self._ordinal, self._seed, self._lane_offset, self._rng_kind, flags)
+    self._lib = self._handle.lib
+    n = ctypes.c_int32()
+    _lib.check(self._lib.bsb_info_count(self._handle.ptr, ctypes.byref(n)))
+    self._info_names = tuple(self._lib.bsb_info_name(self._handle.ptr, k).decode() for k in range(n.value))
+    self.bsuite_num_episodes = spec.bsuite_num_episodes
+
+  # ---- metadata ------------------------------------------------------------
+  batch = property(lambda self: self._batch)
+  device = property(lambda self: self._device)
+  seed = property(lambda self: self._seed)
+  lane_offset = property(lambda self: self._lane_offset)
+  obs_shape = property(lambda self: self._spec.obs_shape)
+  num_actions = property(lambda self: self._spec.num_actions)
+  info_names = property(lambda self: self._info_names)
+
+  def observation_spec(self):
+    """Per-lane spec, identical to the reference environment's."""
+    if self._spec.obs_bounds is not None:
+      lo, hi = self._spec.obs_bounds
+      return specs.BoundedArray(shape=self._spec.obs_shape, dtype=np.float32, name=self._spec.obs_spec_name,
+                                minimum=lo, maximum=hi)
+    return specs.Array(shape=self._spec.obs_shape, dtype=np.float32, name=self._spec.obs_spec_name)
+
+  def action_spec(self):
+    return specs.DiscreteArray(self._spec.num_actions, dtype=self._spec.action_dtype, name='action')
+
+  # ---- buffers -------------------------------------------------------------
+  def make_buffers(self, num_steps: Optional[int] = None, with_actions: bool = False) -> StepBuffers:
+    torch = self._torch
+    lead = (self._batch,) if num_steps is None else (int(num_steps), self._batch)
+    kw = dict(device=self._device)
+    return StepBuffers(
+        observation=torch.empty(lead + tuple(self._spec.obs_shape), dtype=torch.float32, **kw),
+        reward=torch.empty(lead, dtype=self._reward_dtype, **kw),
+        discount=torch.empty(lead, dtype=torch.float32, **kw),
+        step_type=torch.empty(lead, dtype=torch.int32, **kw),
+        actions=torch.empty(lead, dtype=torch.int32, **kw) if with_actions else None)
+
+  def _stream(self):
+    if self._ordinal < 0:
+      return None
+    return ctypes.c_void_p(self._torch.cuda.current_stream(self._device).cuda_stream)
+
+  def _device_actions(self, actions, shape):
+    torch = self._torch
+    if not isinstance(actions, torch.Tensor):
+      actions = torch.as_tensor(np.asarray(actions))
+    if tuple(actions.shape) != tuple(shape):
+      raise ValueError(f'actions must have shape {tuple(shape)}, got {tuple(actions.shape)}')
+    if actions.dtype != torch.int32 or actions.device != self._device or not actions.is_contiguous():
+      actions = actions.to(device=self._device, dtype=torch.int32, non_blocking=True).contiguous()
+    return actions
+
+  # ---- dynamics ------------------------------------------------------------
+  def reset(self, out: Optional[StepBuffers] = None):
+    """base.Environment.reset for every lane (base.py:54-57)."""
+    out = out or self.make_buffers()
+    outputs = out.as_outputs()
+    _lib.check(self._lib.bsb_reset(self._handle.ptr, ctypes.byref(outputs), self._stream()))
+    return out.timestep()
+
+  def step(self, actions, out: Optional[StepBuffers] = None):
+    """base.Environment.step for every lane (base.py:59-65); actions int [B]."""
+    actions = self._device_actions(actions, (self._batch,))
+    out = out or self.make_buffers()
+    outputs = out.as_outputs()
+    _lib.check(self._lib.bsb_step(self._handle.ptr, ctypes.c_void_p(actions.data_ptr()), ctypes.byref(outputs),
+                                  self._stream()))
+    return out.timestep()
+
+  def rollout(self, num_steps: int, actions=None, action_seed: int = 0, out: Optional[StepBuffers] = None):
+    """`num_steps` fused step() calls; actions [T,B] or None for on-device uniform random actions.
+
+    Returns a TimeStep with a leading T axis; when `out.actions` is set it receives the actions used.
+    """
+    num_steps = int(num_steps)
+    out = out or self.make_buffers(num_steps, with_actions=actions is None)
+    act_ptr = None
+    if actions is not None:
+      actions = self._device_actions(actions, (num_steps, self._batch))
+      act_ptr = ctypes.c_void_p(actions.data_ptr())
+    outputs = out.as_outputs()
+    act_out = ctypes.c_void_p(out.actions.data_ptr()) if out.actions is not None else None
+    _lib.check(self._lib.bsb_rollout(self._handle.ptr, num_steps, act_ptr, int(action_seed) & _MASK64,
+                                     ctypes.byref(outputs), act_out, self._stream()))
+    return out.timestep()
+
+  def random_actions(self, num_steps: int, action_seed: int = 0, first_step: Optional[int] = None) -> np.ndarray:
+    """Host mirror of the on-device action sampler for this environment's lanes."""
+    if first_step is None:
+      first_step = self.steps_done
+    out = np.empty((int(num_steps), self._batch), dtype=np.int32)
+    _lib.check(self._lib.bsb_random_actions(int(action_seed) & _MASK64, self._lane_offset, self._batch,
+                                            int(first_step), int(num_steps), self._spec.num_actions,
+                                            ctypes.c_void_p(out.ctypes.data)))
+    return out
+
+  @property
+  def steps_done(self) -> int:
+    n = ctypes.c_int64()
+    _lib.check(self._lib.bsb_steps_done(self._handle.ptr, ctypes.byref(n)))
+    return n.value
+
+  # ---- accumulators ----------------------------------------------------------
+  def bsuite_info(self) -> Dict[str, Any]:
+    """Per-lane `bsuite_info()` accumulators as float64 tensors [B]."""
+    torch = self._torch
+    result = {}
+    for k, name in enumerate(self._info_names):
+      dst = torch.empty(self._batch, dtype=torch.float64, device=self._device)
+      _lib.check(self._lib.bsb_read_info(self._handle.ptr, k, ctypes.c_void_p(dst.data_ptr()), self._stream()))
+      result[name] = dst
+    return result
+
+  def episode_stats(self) -> Dict[str, Any]:
+    """Logging-wrapper columns (utils/wrappers.py:85-110) per lane, float64 [B]."""
+    if not self._track:
+      raise RuntimeError('create the environment with track_episodes=True')
+    torch = self._torch
+    result = {}
+    for k, name in enumerate(_lib.EPISODE_STAT_FIELDS):
+      dst = torch.empty(self._batch, dtype=torch.float64, device=self._device)
+      _lib.check(self._lib.bsb_read_episode_stats(self._handle.ptr, k, ctypes.c_void_p(dst.data_ptr()), self._stream()))
+      result[name] = dst
+    return result
+
+  # ---- checkpoint ------------------------------------------------------------
+  def state_dict(self) -> Dict[str, Any]:
+    n = ctypes.c_int64()
+    _lib.check(self._lib.bsb_state_bytes(self._handle.ptr, ctypes.byref(n)))
+    blob = np.empty(n.value, dtype=np.uint8)
+    _lib.check(self._lib.bsb_get_state(self._handle.ptr, ctypes.c_void_p(blob.ctypes.data), n.value, self._stream()))
+    return dict(blob=blob, batch=self._batch, seed=self._seed, lane_offset=self._lane_offset,
+                family=self._spec.family)
+
+  def load_state_dict(self, state: Dict[str, Any]):
+    if (state['batch'], state['family']) != (self._batch, self._spec.family):
+      raise ValueError('state_dict belongs to a different environment')
+    if (state['seed'], state['lane_offset']) != (self._seed, self._lane_offset):
+      raise ValueError('state_dict was taken with different (seed, lane_offset); RNG keys would not match')
+    blob = np.ascontiguousarray(state['blob'], dtype=np.uint8)
+    _lib.check(self._lib.bsb_set_state(self._handle.ptr, ctypes.c_void_p(blob.ctypes.data), blob.nbytes, self._stream()))
+
+  def close(self):
+    self._handle.close()
+
+
+class DmEnvAdapter(dm_env.Environment):
+  """A single environment instance with the reference's object contract.
+
+  Replaces `bsuite.load_from_id(bsuite_id)` / `bsuite.load(name, kwargs)`
+  (bsuite/bsuite.py:93-108) for unmodified agents: numpy float32 observation,
+  Python float reward / discount, `None` reward and discount on FIRST,
+  `bsuite_info()` dict, `bsuite_num_episodes` attribute.
+  """
+
+  def __init__(self, spec: EnvSpec, device='cuda', seed: Optional[int] = None, rng: Optional[str] = None):
+    self._spec = spec
+    self._ordinal = _resolve_device(device)
+    seed = spec.seed if spec.seed is not None else seed
+    if rng is None:
+      rng = 'mt19937'   # numpy.random.RandomState(seed): the unpatched reference's stream
+    self._seed = _fresh_seed() if seed is None else int(seed)
+    rng_kind = _lib.RNG_PHILOX if rng == 'philox' else _lib.RNG_MT19937
+    if rng_kind == _lib.RNG_MT19937 and not 0 <= self._seed < 2**32:
+      raise ValueError('Seed must be between 0 and 2**32 - 1')
+    self._handle = _Handle(spec, 1, self._ordinal, self._seed, 0, rng_kind, 0)
+    self._lib = self._handle.lib
+    n = ctypes.c_int32()
+    _lib.check(self._lib.bsb_info_count(self._handle.ptr, ctypes.byref(n)))
+    self._info_names = tuple(self._lib.bsb_info_name(self._handle.ptr, k).decode() for k in range(n.value))
+    self.bsuite_num_episodes = spec.bsuite_num_episodes
+    numel = int(np.prod(spec.obs_shape))
+    self._obs = np.zeros(numel, dtype=np.float32)
+    self._reward = np.zeros(1, dtype=np.float64)
+    self._discount = np.zeros(1, dtype=np.float32)
+    self._step_type = np.zeros(1, dtype=np.int32)
+    self._action = np.zeros(1, dtype=np.int32)
+    self._outputs = _lib.Outputs()
+    self._outputs.observation = self._obs.ctypes.data
+    self._outputs.reward_f64 = self._reward.ctypes.data
+    self._outputs.discount = self._discount.ctypes.data
+    self._outputs.step_type = self._step_type.ctypes.data
+    self._dev = None
+    if self._ordinal >= 0:   # device-side scratch for reset(); step() uses bsb_step_host
+      import torch
+      device_t = torch.device('cuda', self._ordinal)
+      self._dev = StepBuffers(
+          observation=torch.empty(numel, dtype=torch.float32, device=device_t),
+          reward=torch.empty(1, dtype=torch.float64, device=device_t),
+          discount=torch.empty(1, dtype=torch.float32, device=device_t),
+          step_type=torch.empty(1, dtype=torch.int32, device=device_t))
+
+  def _timestep(self):
+    step_type = dm_env.StepType(int(self._step_type[0]))
+    observation = self._obs.reshape(self._spec.obs_shape).copy()   # caller owns a fresh array
+    if step_type == dm_env.StepType.FIRST:
+      return dm_env.TimeStep(step_type, None, None, observation)
+    return dm_env.TimeStep(step_type, float(self._reward[0]), float(self._discount[0]), observation)
+
+  def reset(self):
+    if self._ordinal < 0:
+      _lib.check(self._lib.bsb_reset(self._handle.ptr, ctypes.byref(self._outputs), None))
+    else:
+      import torch
+      outputs = self._dev.as_outputs()
+      stream = ctypes.c_void_p(torch.cuda.current_stream(self._dev.observation.device).cuda_stream)
+      _lib.check(self._lib.bsb_reset(self._handle.ptr, ctypes.byref(outputs), stream))
+      self._obs[:] = self._dev.observation.cpu().numpy()
+      self._reward[:] = self._dev.reward.cpu().numpy()
+      self._discount[:] = self._dev.discount.cpu().numpy()
+      self._step_type[:] = self._dev.step_type.cpu().numpy()
+    return self._timestep()
+
+  def step(self, action):
+    self._action[0] = int(action)
+    if self._ordinal < 0:
+      _lib.check(self._lib.bsb_step(self._handle.ptr, ctypes.c_void_p(self._action.ctypes.data),
+                                    ctypes.byref(self._outputs), None))
+    else:
+      _lib.check(self._lib.bsb_step_host(self._handle.ptr, ctypes.c_void_p(self._action.ctypes.data),
+                                         ctypes.byref(self._outputs), None))
+    return self._timestep()
+
+  def observation_spec(self):
+    if self._spec.obs_bounds is not None:
+      lo, hi = self._spec.obs_bounds
+      return specs.BoundedArray(shape=self._spec.obs_shape, dtype=np.float32, name=self._spec.obs_spec_name,
+                                minimum=lo, maximum=hi)
+    return specs.Array(shape=self._spec.obs_shape, dtype=np.float32, name=self._spec.obs_spec_name)
+
+  def action_spec(self):
+    return specs.DiscreteArray(self._spec.num_actions, dtype=self._spec.action_dtype, name='action')
+
+  def bsuite_info(self) -> Dict[str, Any]:
+    result = {}
+    for k, name in enumerate(self._info_names):
+      if self._ordinal < 0:
+        value = np.zeros(1, dtype=np.float64)
+        _lib.check(self._lib.bsb_read_info(self._handle.ptr, k, ctypes.c_void_p(value.ctypes.data), None))
+        value = float(value[0])
+      else:
+        import torch
+        dst = torch.empty(1, dtype=torch.float64, device=self._dev.observation.device)
+        _lib.check(self._lib.bsb_read_info(self._handle.ptr, k, ctypes.c_void_p(dst.data_ptr()), None))
+        value = float(dst.cpu()[0])
+      result[name] = int(value) if name in _INT_INFO else value
+    return result
+
+  @property
+  def raw_env(self):
+    return self
+
+  def close(self):
+    self._handle.close()

@@ -1,0 +1,69 @@
+"""`load` / `load_from_id`: the drop-in boundary.
+
+Same names, ids and keyword arguments as `bsuite/bsuite.py:57-108`.  With
+`batch=None` the result is a single `dm_env.Environment` (the reference's
+contract); with `batch=B` it is a `BatchedEnvironment` of B lanes.
+"""
+
+import functools
+from typing import Any, Mapping, Optional, Tuple
+
+from bsuite_b200 import experiments
+from bsuite_b200 import sweep
+from bsuite_b200.environment import BatchedEnvironment, DmEnvAdapter
+
+
+def unpack_bsuite_id(bsuite_id: str) -> Tuple[str, int]:
+  """'deep_sea/11' -> ('deep_sea', 11)   (bsuite.py:84-90)."""
+  name, _, index = bsuite_id.partition(sweep.SEPARATOR)
+  if not name or not index or sweep.SEPARATOR in index:
+    raise ValueError(f'malformed bsuite_id {bsuite_id!r}')
+  return name, int(index)
+
+
+def _instantiate(spec, batch, device, seed, rng, **engine_kwargs):
+  if batch is None:
+    if engine_kwargs:
+      raise TypeError(f'{sorted(engine_kwargs)} only apply to batched environments (pass batch=...)')
+    return DmEnvAdapter(spec, device=device, seed=seed, rng=rng)
+  return BatchedEnvironment(spec, batch=batch, device=device, seed=seed, rng=rng or 'philox', **engine_kwargs)
+
+
+def load(experiment_name: str, kwargs: Mapping[str, Any], batch: Optional[int] = None, device='cuda',
+         seed: Optional[int] = None, rng: Optional[str] = None, **engine_kwargs):
+  """Returns a bsuite environment given an experiment name and settings (bsuite.py:93-98)."""
+  spec = experiments.EXPERIMENT_NAME_TO_SPEC[experiment_name](**kwargs)
+  return _instantiate(spec, batch, device, seed, rng, **engine_kwargs)
+
+
+def load_from_id(bsuite_id: str, batch: Optional[int] = None, device='cuda', seed: Optional[int] = None,
+                 rng: Optional[str] = None, **engine_kwargs):
+  """Returns a bsuite environment given a bsuite_id (bsuite.py:101-108)."""
+  kwargs = sweep.SETTINGS[bsuite_id]
+  experiment_name, _ = unpack_bsuite_id(bsuite_id)
+  return load(experiment_name, kwargs, batch=batch, device=device, seed=seed, rng=rng, **engine_kwargs)
+
+
+def make(environment_class: str, batch: Optional[int] = None, device='cuda', seed: Optional[int] = None,
+         rng: Optional[str] = None, noise_scale: Optional[float] = None, reward_scale: Optional[float] = None,
+         engine_kwargs: Optional[Mapping[str, Any]] = None, **kwargs):
+  """Constructs a raw environment class, e.g. make('deep_sea', size=10, deterministic=False, seed=0).
+
+  `noise_scale` / `reward_scale` wrap it in the fused RewardNoise / RewardScale
+  epilogue (utils/wrappers.py:250-373), as the `*_noise` / `*_scale` factories do.
+  """
+  spec = experiments.ENVIRONMENT_CLASSES[environment_class](**kwargs)
+  if noise_scale is not None and reward_scale is not None:
+    raise ValueError('at most one reward wrapper')
+  if noise_scale is not None:
+    spec = experiments._with_noise(spec, noise_scale, spec.bsuite_num_episodes)  # pylint: disable=protected-access
+  if reward_scale is not None:
+    spec = experiments._with_scale(spec, reward_scale, spec.bsuite_num_episodes)  # pylint: disable=protected-access
+  return _instantiate(spec, batch, device, seed, rng, **(engine_kwargs or {}))
+
+
+# experiment name -> loader accepting that experiment's kwargs (bsuite.py:57-81)
+EXPERIMENT_NAME_TO_ENVIRONMENT = {
+    name: functools.partial(lambda _name, **kw: load(_name, kw), name)
+    for name in experiments.EXPERIMENT_NAME_TO_SPEC
+}
