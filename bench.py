@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the batched bsuite engine on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA engine
+    python bench.py --impl reference [--steps K] [--warmup W]      # the reference's CPU algorithm on host cores
+    torchrun --nproc-per-node N ... bench.py --gpus N ...           # one rank per GPU (weak scaling)
+
+Workload (BASELINE.json configs[1]): deep_sea size=32 (bsuite_id deep_sea/11), 65 536 lanes per GPU, uniform
+random actions.  One "step" = one lock-step `step()` call over the whole batch = ONE kernel launch that writes a
+fresh dense [B, 32, 32] float32 observation tensor (268 MB) plus reward / discount / step_type.
+
+  value   : env-steps/s with actions already resident in HBM; outputs go to a ring of 4 buffer sets (1.07 GB of
+            observations > 126 MB L2, so every step's stores reach HBM); CUDA-event timed, max over ranks.
+  e2e     : the same metric through the public Python API with HOST actions (pinned) copied H2D inside the timed
+            region and reward / discount / step_type copied D2H every step (observations stay on the device for
+            the agent, which is the engine's contract); `host_obs_value` additionally copies the 268 MB of
+            observations to pinned host memory every step (PCIe-bound).
+  roofline: algorithmic bytes per launch (4 120 B per lane-step) / mean launch duration, against
+            MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline: the numpy restatement of the reference (oracle/bsuite_oracle.py, kind "port") stepping the same
+            workload on all host cores for a bounded sample.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+  sys.path.insert(0, ROOT)
+
+BSUITE_ID = 'deep_sea/11'          # size = 32, mapping_seed = 42
+SIZE = 32
+BATCH_PER_GPU = 65536
+ALGO_BYTES_PER_LANE_STEP = 4 * SIZE * SIZE + 4 + 4 + 4 + 4 + 4 + 4   # obs + action + reward + discount + step_type + state rd/wr
+RING = 4
+METRIC = 'env-steps/sec'
+FALLBACK_HBM_GBS = 6650.0
+
+
+# ----------------------------------------------------------------------------- reference arm / cpu baseline
+def _reference_worker(job):
+  """Steps `lanes` independent oracle environments `warmup + steps` times; returns the timed seconds."""
+  lanes, steps, warmup, first_lane = job
+  import numpy as np
+  from oracle import bsuite_oracle as oracle
+  envs = [oracle.OracleEnv('deep_sea', dict(size=SIZE, mapping_seed=42), rng='philox', seed=0, lane=first_lane + i)
+          for i in range(lanes)]
+  actions = np.random.RandomState(first_lane).randint(2, size=(warmup + steps, lanes))
+  for t in range(warmup):
+    row = actions[t]
+    for i, env in enumerate(envs):
+      env.step(int(row[i]))
+  start = time.perf_counter()
+  for t in range(warmup, warmup + steps):
+    row = actions[t]
+    for i, env in enumerate(envs):
+      env.step(int(row[i]))
+  return time.perf_counter() - start
+
+
+def _calibrate_reference() -> float:
+  """Seconds per single-environment step() of the oracle port (one core)."""
+  import numpy as np
+  from oracle import bsuite_oracle as oracle
+  env = oracle.OracleEnv('deep_sea', dict(size=SIZE, mapping_seed=42), rng='philox', seed=0, lane=0)
+  actions = np.random.RandomState(0).randint(2, size=3000)
+  for a in actions[:500]:
+    env.step(int(a))
+  start = time.perf_counter()
+  for a in actions[500:]:
+    env.step(int(a))
+  return (time.perf_counter() - start) / 2500
+
+
+def run_reference_sample(steps: int, warmup: int, budget_s: float = 20.0):
+  """The reference's algorithm on every host core, one process per core (mirrors baselines/utils/pool.py:28-54)."""
+  import multiprocessing as mp
+  cores = os.cpu_count() or 1
+  per_step = _calibrate_reference()
+  if steps <= 0:   # auto: the whole batch split over the cores, as many steps as fit the time budget
+    lanes = max(1, BATCH_PER_GPU // cores)
+    steps = max(10, int(budget_s / (lanes * per_step)))
+  else:
+    lanes = int(budget_s / ((steps + warmup) * per_step))
+    lanes = max(1, min(lanes, BATCH_PER_GPU // cores))
+  jobs = [(lanes, steps, warmup, w * lanes) for w in range(cores)]
+  with mp.get_context('spawn').Pool(cores) as pool:
+    seconds = pool.map(_reference_worker, jobs)
+  total_steps = cores * lanes * steps
+  slowest = max(seconds)
+  return dict(value=total_steps / slowest, cores=cores, lanes=cores * lanes, steps=steps, seconds=slowest,
+              single_core_steps_per_s=1.0 / per_step)
+
+
+def reference_main(args):
+  rank = int(os.environ.get('RANK', '0'))
+  if rank != 0:
+    return 0
+  r = run_reference_sample(args.steps, args.warmup, budget_s=12.0 if args.steps <= 0 else 20.0)
+  args.steps = r['steps']
+  sample = (f"{r['lanes']} of {BATCH_PER_GPU} lanes x {r['steps']} steps, one process per core "
+            f"({r['cores']} cores), numpy restatement of bsuite DeepSea.step")
+  line = {
+      'metric': METRIC, 'value': r['value'], 'unit': 'env-steps/s', 'n_gpus': args.gpus, 'steps': args.steps,
+      'warmup': args.warmup, 'ms_per_step': 1e3 * r['seconds'] / r['steps'], 'higher_is_better': True,
+      'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'impl': 'reference',
+      'config': {'workload': f'deep_sea size={SIZE} ({BSUITE_ID}) uniform random actions, CPU sample of the '
+                             f'{BATCH_PER_GPU}-lane batch', 'sample_lanes': r['lanes']},
+      'cpu_baseline': {'value': r['value'], 'unit': 'env-steps/s', 'cores': r['cores'], 'kind': 'port',
+                       'sample': sample, 'single_core': r['single_core_steps_per_s']},
+      'e2e': {'value': r['value'], 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+      'gpu_launches': 0,
+  }
+  print(json.dumps(line))
+  return 0
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+  """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+  QUERY = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+           'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+           'clocks_event_reasons.sw_power_cap')
+
+  def __init__(self, index: int):
+    self.index, self.proc, self.lines = index, None, []
+
+  def start(self):
+    try:
+      self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits',
+                                    '-lms', '100', '-i', str(self.index)], stdout=subprocess.PIPE,
+                                   stderr=subprocess.DEVNULL, text=True)
+      self.thread = threading.Thread(target=self._pump, daemon=True)
+      self.thread.start()
+    except OSError:
+      self.proc = None
+
+  def _pump(self):
+    for line in self.proc.stdout:
+      self.lines.append(line.strip())
+
+  def stop(self):
+    if self.proc is None:
+      return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+    time.sleep(0.15)
+    self.proc.terminate()
+    try:
+      self.proc.wait(timeout=2)
+    except subprocess.TimeoutExpired:
+      self.proc.kill()
+    sm, mx, reasons, power = [], [], set(), []
+    names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
+    for line in self.lines:
+      parts = [p.strip() for p in line.split(',')]
+      if len(parts) < 7:
+        continue
+      try:
+        sm.append(float(parts[0])); mx.append(float(parts[1])); power.append(float(parts[2]))
+      except ValueError:
+        continue
+      for name, flag in zip(names, parts[3:7]):
+        if flag.lower().startswith('active'):
+          reasons.add(name)
+    if not sm:
+      return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples']}
+    sm.sort()
+    return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': max(mx), 'reasons': sorted(reasons), 'samples': len(sm),
+            'power_w_max': max(power)}
+
+
+# ----------------------------------------------------------------------------- engine arm
+def engine_main(args):
+  import torch
+  import torch.distributed as dist
+  import bsuite_b200
+  from bsuite_b200 import _lib
+
+  rank = int(os.environ.get('RANK', '0'))
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+  if not torch.cuda.is_available():
+    raise RuntimeError('bench.py measures the CUDA engine; no CUDA device is visible (use --impl reference for the CPU arm)')
+  torch.cuda.set_device(local_rank)
+  device = torch.device('cuda', local_rank)
+  if world > 1:
+    dist.init_process_group('nccl', device_id=device)
+  if args.gpus != world:
+    raise SystemExit(f'--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}')
+
+  # cpu_baseline first (rank 0, N = 1 only), in a clean subprocess so worker processes never inherit CUDA state
+  cpu_baseline = None
+  if rank == 0 and world == 1 and not args.skip_cpu_baseline:
+    proc = subprocess.run([sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', '0',
+                           '--warmup', '3'], capture_output=True, text=True, env=dict(os.environ, CUDA_VISIBLE_DEVICES=''))
+    try:
+      cpu_baseline = json.loads(proc.stdout.strip().splitlines()[-1])['cpu_baseline']
+    except Exception:  # pylint: disable=broad-except
+      cpu_baseline = {'value': None, 'unit': 'env-steps/s', 'cores': os.cpu_count(), 'kind': 'port',
+                      'sample': 'failed: ' + (proc.stderr or '')[-300:]}
+
+  B, K, W = BATCH_PER_GPU, args.steps, args.warmup
+  lib = _lib.load()
+  env = bsuite_b200.load_from_id(BSUITE_ID, batch=B, device=device, seed=0, lane_offset=rank * B,
+                                 track_episodes=not args.no_track)
+  ring = [env.make_buffers() for _ in range(RING)]
+  gen = torch.Generator(device=device)
+  gen.manual_seed(1234 + rank)
+  actions = torch.randint(0, 2, (W + K, B), generator=gen, device=device, dtype=torch.int32)
+
+  def log_point():
+    """Device-side reduction of the Logging accumulators + one all-gather of per-rank episode returns."""
+    if args.no_track:
+      return None
+    stats = env.episode_stats()
+    block = torch.stack([stats['total_return'].sum(), stats['episode'].sum(), stats['steps'].sum()])
+    if world > 1:
+      gathered = torch.empty(world * 3, dtype=block.dtype, device=device)
+      dist.all_gather_into_tensor(gathered, block)
+      return gathered
+    return block
+
+  # ---- value: device-resident actions -------------------------------------
+  for t in range(W):
+    env.step(actions[t], out=ring[t % RING])
+  log_point()
+  torch.cuda.synchronize()
+  if world > 1:
+    dist.barrier()
+  torch.cuda.synchronize()
+  sampler = ClockSampler(local_rank)
+  if rank == 0:
+    sampler.start()
+  launches0 = lib.bsb_launch_count()
+  ev0, ev1, ev2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+  ev0.record()
+  for t in range(K):
+    env.step(actions[W + t], out=ring[t % RING])
+  ev1.record()
+  summary = log_point()
+  ev2.record()
+  torch.cuda.synchronize()
+  if world > 1:
+    dist.barrier()
+  torch.cuda.synchronize()
+  launches = lib.bsb_launch_count() - launches0
+  clocks = sampler.stop() if rank == 0 else None
+  step_ms = ev0.elapsed_time(ev1)        # K kernel launches back to back
+  total_ms = ev0.elapsed_time(ev2)       # + the log point (reduction, all-gather)
+  times = torch.tensor([total_ms, step_ms], dtype=torch.float64, device=device)
+  if world > 1:
+    dist.all_reduce(times, op=dist.ReduceOp.MAX)
+  total_ms, step_ms = float(times[0]), float(times[1])
+  value = world * B * K / (total_ms * 1e-3)
+
+  # ---- e2e: host actions in, scalars out, every step ---------------------------
+  Ke = max(10, min(K, 200))
+  host_actions = torch.randint(0, 2, (Ke, B), dtype=torch.int32).pin_memory()
+  host_out = {k: torch.empty(B, dtype=dt).pin_memory() for k, dt in
+              (('reward', torch.float32), ('discount', torch.float32), ('step_type', torch.int32))}
+
+  def e2e_loop(n, copy_obs, host_obs=None):
+    for t in range(n):
+      ts = env.step(host_actions[t % Ke], out=ring[t % RING])      # public API: H2D of the pinned actions inside
+      host_out['reward'].copy_(ts.reward, non_blocking=True)
+      host_out['discount'].copy_(ts.discount, non_blocking=True)
+      host_out['step_type'].copy_(ts.step_type, non_blocking=True)
+      if copy_obs:
+        host_obs.copy_(ts.observation, non_blocking=True)
+      torch.cuda.synchronize()                                      # the agent reads the result before acting again
+
+  e2e_loop(3, False)
+  if world > 1:
+    dist.barrier()
+  torch.cuda.synchronize()
+  t0 = time.perf_counter()
+  e2e_loop(Ke, False)
+  e2e_s = time.perf_counter() - t0
+  e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
+  if world > 1:
+    dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+  e2e_value = world * B * Ke / float(e2e_t[0])
+  host_obs_value = None
+  if not args.skip_host_obs:
+    host_obs = torch.empty((B, SIZE, SIZE), dtype=torch.float32).pin_memory()
+    e2e_loop(2, True, host_obs)
+    t0 = time.perf_counter()
+    e2e_loop(5, True, host_obs)
+    ho = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+    if world > 1:
+      dist.all_reduce(ho, op=dist.ReduceOp.MAX)
+    host_obs_value = world * B * 5 / float(ho[0])
+
+  if rank == 0:
+    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(peaks_path):
+      peak, peak_src = float(json.load(open(peaks_path))['hbm_gbs']), 'MEASURED_PEAKS.json hbm_gbs (measured copy)'
+    else:
+      peak, peak_src = FALLBACK_HBM_GBS, 'fallback 6.65 TB/s (B200_PROFILING.md)'
+    launch_s = (step_ms * 1e-3) / K
+    achieved = ALGO_BYTES_PER_LANE_STEP * B / launch_s / 1e9
+    line = {
+        'metric': METRIC, 'value': value, 'unit': 'env-steps/s', 'n_gpus': world, 'steps': K, 'warmup': W,
+        'ms_per_step': total_ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': f'deep_sea size={SIZE} batch={B} per GPU ({BSUITE_ID}), uniform random actions',
+                   'bsuite_id': BSUITE_ID, 'batch_per_gpu': B, 'global_batch': world * B,
+                   'parallelism': f'lanes sharded over {world} GPU(s), no data-path collective; one all-gather of '
+                                  'per-rank episode returns at the log point inside the timed region',
+                   'l2_policy': f'outputs cycle through {RING} buffer sets ({RING * B * SIZE * SIZE * 4 / 1e9:.2f} GB '
+                                'of observations > 126 MB L2)',
+                   'launch': 'one transition_kernel launch per step (T = 1)',
+                   'track_episodes': not args.no_track},
+        'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                     'traffic': None, 'peak_source': peak_src,
+                     'algorithmic_bytes_per_launch': ALGO_BYTES_PER_LANE_STEP * B,
+                     'launch_us': launch_s * 1e6, 'kernel': 'transition_kernel<DeepSea, Philox, no-noise>'},
+        'cpu_baseline': cpu_baseline,
+        'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 4 * B, 'd2h_bytes_per_step': 12 * B,
+                'steps': Ke, 'host_obs_value': host_obs_value,
+                'host_obs_d2h_bytes_per_step': 4 * B * SIZE * SIZE + 12 * B,
+                'note': 'value: observations stay on the device (the API contract); host_obs_value also copies them out'},
+        'gpu_launches': int(launches),
+        'clocks': clocks,
+        'log_point': None if summary is None else [float(x) for x in summary.cpu()[:3]],
+    }
+    print(json.dumps(line))
+  if world > 1:
+    dist.destroy_process_group()
+  return 0
+
+
+def main():
+  parser = argparse.ArgumentParser()
+  parser.add_argument('--gpus', type=int, default=1)
+  parser.add_argument('--steps', type=int, default=400)
+  parser.add_argument('--warmup', type=int, default=20)
+  parser.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+  parser.add_argument('--skip-cpu-baseline', action='store_true')
+  parser.add_argument('--skip-host-obs', action='store_true')
+  parser.add_argument('--no-track', action='store_true', help='disable the per-lane Logging accumulators')
+  args = parser.parse_args()
+  if args.warmup < 3:
+    args.warmup = 3
+  if args.impl == 'reference':
+    return reference_main(args)
+  return engine_main(args)
+
+
+if __name__ == '__main__':
+  sys.exit(main())
