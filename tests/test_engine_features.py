@@ -1,0 +1,157 @@
+"""Engine features beyond single steps: fused rollouts with on-device actions, Logging accumulators,
+state snapshots, edge cases (ragged batches, B = 1, unaligned tiles).  Each test runs on the explicit host path
+here and on the CUDA path on the GPU box (-m gpu), always checked against the oracle."""
+
+import numpy as np
+import pytest
+import torch
+
+import bsuite_b200
+from oracle import bsuite_oracle as oracle
+from oracle import reference_runner as rr
+
+DEVICES = [pytest.param('cpu', id='host'), pytest.param('cuda', id='cuda', marks=pytest.mark.gpu)]
+
+
+def _np(t):
+  return t.cpu().numpy()
+
+
+@pytest.mark.parametrize('device', DEVICES)
+@pytest.mark.parametrize('env_class,kwargs,batch', [
+    ('deep_sea', dict(size=10, mapping_seed=42), 77),          # ragged: 2 full warps + 13 lanes
+    ('deep_sea', dict(size=7, deterministic=False, mapping_seed=1), 33),   # odd N: unaligned tiles
+    ('catch', dict(), 45),
+    ('catch', dict(rows=3, columns=3), 1),
+    ('umbrella_chain', dict(chain_length=4, n_distractor=5), 40),
+    ('memory_chain', dict(memory_length=3, num_bits=64), 9),    # maximum context width
+    ('discounting_chain', dict(mapping_seed=1), 65),
+    ('bandit', dict(mapping_seed=5), 31),
+])
+def test_rollout_with_device_sampled_actions_matches_oracle(device, env_class, kwargs, batch):
+  """Actions sampled ON DEVICE by the Philox action stream; `random_actions` is the host mirror; the whole
+  trajectory must equal the oracle fed the same actions, for every lane (integer families: bit-exact)."""
+  T, seed, action_seed, offset = 37, 123, 9, 1000
+  env = bsuite_b200.make(env_class, batch=batch, device=device, seed=seed,
+                         engine_kwargs=dict(reward_dtype='float64', lane_offset=offset), **kwargs)
+  mirror = env.random_actions(T, action_seed=action_seed)
+  out = env.make_buffers(T, with_actions=True)
+  ts = env.rollout(T, action_seed=action_seed, out=out)
+  np.testing.assert_array_equal(_np(out.actions), mirror)
+  assert mirror.min() >= 0 and mirror.max() < env.num_actions
+  want = oracle.run_lanes(env_class, kwargs, mirror, rng='philox', seed=seed, lane_offset=offset)
+  np.testing.assert_array_equal(_np(ts.step_type), want['step_type'])
+  np.testing.assert_array_equal(_np(ts.observation), want['observation'])
+  np.testing.assert_array_equal(_np(ts.discount), want['discount'])
+  if env_class == 'deep_sea' and not kwargs.get('deterministic', True) and device != 'cpu':
+    np.testing.assert_allclose(_np(ts.reward), want['reward'], rtol=1e-12, atol=1e-12)   # log() in randn
+  else:
+    np.testing.assert_array_equal(_np(ts.reward), want['reward'])
+  for k, v in env.bsuite_info().items():
+    np.testing.assert_array_equal(_np(v), want['info'][k], err_msg=k)
+  # a second rollout continues both the environment and the action stream
+  assert env.steps_done == T
+  ts2 = env.rollout(5, action_seed=action_seed)
+  mirror2 = env.random_actions(5, action_seed=action_seed, first_step=T)
+  want2 = oracle.run_lanes(env_class, kwargs, np.concatenate([mirror, mirror2]), rng='philox', seed=seed, lane_offset=offset)
+  np.testing.assert_array_equal(_np(ts2.step_type), want2['step_type'][T:])
+  np.testing.assert_array_equal(_np(ts2.observation), want2['observation'][T:])
+  env.close()
+
+
+@pytest.mark.parametrize('device', DEVICES)
+def test_action_sampler_is_uniform_and_shard_invariant(device):
+  env = bsuite_b200.load_from_id('catch/0', batch=4096, device=device, seed=0)
+  acts = env.random_actions(64, action_seed=3)
+  counts = np.bincount(acts.ravel(), minlength=3) / acts.size
+  assert np.all(np.abs(counts - 1 / 3) < 0.01)
+  shard = bsuite_b200.load_from_id('catch/0', batch=100, device=device, seed=0, lane_offset=1000)
+  np.testing.assert_array_equal(shard.random_actions(64, action_seed=3), acts[:, 1000:1100])
+
+
+@pytest.mark.parametrize('device', DEVICES)
+def test_state_snapshot_restores_trajectory(device):
+  """get/set_state (checkpoint-resume): restoring a snapshot replays the same future."""
+  env = bsuite_b200.load_from_id('catch_noise/3', batch=50, device=device, seed=4, track_episodes=True,
+                                 reward_dtype='float64')
+  actions = torch.as_tensor(np.random.RandomState(0).randint(3, size=(40, 50)).astype(np.int32))
+  env.rollout(13, actions=actions[:13])
+  snapshot = env.state_dict()
+  a = env.rollout(27, actions=actions[13:])
+  a = {k: _np(getattr(a, k)).copy() for k in ('step_type', 'reward', 'observation')}
+  info_a = {k: _np(v).copy() for k, v in env.bsuite_info().items()}
+  env.load_state_dict(snapshot)
+  assert env.steps_done == 13
+  b = env.rollout(27, actions=actions[13:])
+  for k in a:
+    np.testing.assert_array_equal(a[k], _np(getattr(b, k)))
+  for k, v in env.bsuite_info().items():
+    np.testing.assert_array_equal(info_a[k], _np(v))
+  other = bsuite_b200.load_from_id('catch_noise/3', batch=50, device=device, seed=5)
+  with pytest.raises(ValueError):
+    other.load_state_dict(snapshot)
+
+
+class _Recorder:
+  def __init__(self):
+    self.rows = []
+
+  def write(self, data):
+    self.rows.append(dict(data))
+
+
+@pytest.mark.parametrize('device', DEVICES)
+def test_episode_stats_match_reference_logging_wrapper(device):
+  """The per-lane Logging accumulators (utils/wrappers.py:85-110) against the reference's own wrapper when it is
+  available, else against the same bookkeeping applied to the oracle trace."""
+  kwargs, seed, T, B = dict(rows=5, columns=3), 21, 90, 6
+  env = bsuite_b200.make('catch', batch=B, device=device, seed=seed, reward_scale=30.0,
+                         engine_kwargs=dict(reward_dtype='float64', track_episodes=True), **kwargs)
+  actions = np.random.RandomState(2).randint(3, size=(T, B)).astype(np.int32)
+  env.rollout(T, actions=torch.as_tensor(actions))
+  stats = {k: _np(v) for k, v in env.episode_stats().items()}
+  want = oracle.run_lanes('catch', kwargs, actions, rng='philox', seed=seed, wrapper='scale', wrapper_arg=30.0)
+  for lane in range(B):
+    steps = episode = ep_len = 0
+    total = ep_ret = 0.0
+    last_len, last_ret = 0, 0.0
+    for t in range(T):
+      st, r = want['step_type'][t, lane], want['reward'][t, lane]
+      if st != 0:
+        steps += 1; ep_len += 1
+      if st == 2:
+        episode += 1
+      ep_ret += r if st != 0 else 0.0
+      total += r if st != 0 else 0.0
+      if st == 2:
+        last_len, last_ret, ep_len, ep_ret = ep_len, ep_ret, 0, 0.0
+    got = [stats[k][lane] for k in ('steps', 'episode', 'total_return', 'episode_len', 'episode_return',
+                                    'last_episode_len', 'last_episode_return')]
+    assert got == [steps, episode, total, ep_len, ep_ret, last_len, last_ret]
+  if rr.reference_available():
+    rr.import_reference()
+    from bsuite.utils import wrappers  # pylint: disable=import-outside-toplevel
+    for lane in range(B):
+      raw = rr.make_reference_env('catch', kwargs, 'philox', seed, lane, 'scale', 30.0)
+      raw.bsuite_num_episodes = 10**9
+      recorder = _Recorder()
+      logged = wrappers.Logging(raw, recorder, log_every=True)
+      for t in range(T):
+        logged.step(int(actions[t, lane]))
+      final = recorder.rows[-1]     # written at the most recent LAST timestep
+      assert final['episode'] == stats['episode'][lane]
+      assert final['episode_len'] == stats['last_episode_len'][lane]
+      assert final['episode_return'] == stats['last_episode_return'][lane]
+      assert final['total_regret'] == _np(env.bsuite_info()['total_regret'])[lane]
+
+
+@pytest.mark.parametrize('device', DEVICES)
+def test_unsupported_configurations_are_rejected(device):
+  from bsuite_b200 import _lib
+  with pytest.raises(_lib.EngineError, match='num_bits'):
+    bsuite_b200.make('memory_chain', batch=4, device=device, memory_length=2, num_bits=65)
+  with pytest.raises(_lib.EngineError, match='size'):
+    bsuite_b200.make('deep_sea', batch=4, device=device, size=300)
+  env = bsuite_b200.load_from_id('catch/0', batch=4, device=device)
+  with pytest.raises(ValueError, match='shape'):
+    env.step(torch.zeros(5, dtype=torch.int32))
