@@ -122,8 +122,8 @@ def reference_main(args):
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
-  """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
-  QUERY = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+  """Samples nvidia-smi clocks / throttle reasons; `stop(t0, t1)` keeps the samples taken under load."""
+  QUERY = ('timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
            'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
            'clocks_event_reasons.sw_power_cap')
 
@@ -133,7 +133,7 @@ class ClockSampler:
   def start(self):
     try:
       self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits',
-                                    '-lms', '100', '-i', str(self.index)], stdout=subprocess.PIPE,
+                                    '-lms', '50', '-i', str(self.index)], stdout=subprocess.PIPE,
                                    stderr=subprocess.DEVNULL, text=True)
       self.thread = threading.Thread(target=self._pump, daemon=True)
       self.thread.start()
@@ -144,10 +144,15 @@ class ClockSampler:
     for line in self.proc.stdout:
       self.lines.append(line.strip())
 
-  def stop(self):
+  def wait_first_sample(self, timeout=5.0):
+    end = time.time() + timeout
+    while self.proc is not None and not self.lines and time.time() < end:
+      time.sleep(0.02)
+
+  def stop(self, t0=None, t1=None):
+    import datetime
     if self.proc is None:
       return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-    time.sleep(0.15)
     self.proc.terminate()
     try:
       self.proc.wait(timeout=2)
@@ -157,20 +162,23 @@ class ClockSampler:
     names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
     for line in self.lines:
       parts = [p.strip() for p in line.split(',')]
-      if len(parts) < 7:
+      if len(parts) < 8:
         continue
       try:
-        sm.append(float(parts[0])); mx.append(float(parts[1])); power.append(float(parts[2]))
+        stamp = datetime.datetime.strptime(parts[0], '%Y/%m/%d %H:%M:%S.%f').timestamp()
+        if t0 is not None and not (t0 <= stamp <= t1):
+          continue
+        sm.append(float(parts[1])); mx.append(float(parts[2])); power.append(float(parts[3]))
       except ValueError:
         continue
-      for name, flag in zip(names, parts[3:7]):
+      for name, flag in zip(names, parts[4:8]):
         if flag.lower().startswith('active'):
           reasons.add(name)
     if not sm:
-      return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples']}
+      return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples'], 'raw_lines': len(self.lines)}
     sm.sort()
-    return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': max(mx), 'reasons': sorted(reasons), 'samples': len(sm),
-            'power_w_max': max(power)}
+    return {'sm_mhz': sm[len(sm) // 2], 'sm_mhz_min': sm[0], 'sm_max_mhz': max(mx), 'reasons': sorted(reasons),
+            'samples_under_load': len(sm), 'power_w_max': max(power)}
 
 
 # ----------------------------------------------------------------------------- engine arm
@@ -225,16 +233,30 @@ def engine_main(args):
     return block
 
   # ---- value: device-resident actions -------------------------------------
+  sampler = ClockSampler(local_rank)
+  if rank == 0:
+    sampler.start()
+    sampler.wait_first_sample()
+
+  def keep_busy(seconds):
+    """Untimed steps of the same workload, so the clock samples bracket the timed region under load."""
+    end = time.time() + seconds
+    t = 0
+    while time.time() < end:
+      for _ in range(50):
+        env.step(actions[t % (W + K)], out=ring[t % RING])
+        t += 1
+      torch.cuda.synchronize()
+
+  load_t0 = time.time()
   for t in range(W):
     env.step(actions[t], out=ring[t % RING])
+  keep_busy(0.5)
   log_point()
   torch.cuda.synchronize()
   if world > 1:
     dist.barrier()
   torch.cuda.synchronize()
-  sampler = ClockSampler(local_rank)
-  if rank == 0:
-    sampler.start()
   launches0 = lib.bsb_launch_count()
   ev0, ev1, ev2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
   ev0.record()
@@ -248,7 +270,8 @@ def engine_main(args):
     dist.barrier()
   torch.cuda.synchronize()
   launches = lib.bsb_launch_count() - launches0
-  clocks = sampler.stop() if rank == 0 else None
+  keep_busy(0.4)
+  clocks = sampler.stop(load_t0 + 0.15, time.time()) if rank == 0 else None
   step_ms = ev0.elapsed_time(ev1)        # K kernel launches back to back
   total_ms = ev0.elapsed_time(ev2)       # + the log point (reduction, all-gather)
   times = torch.tensor([total_ms, step_ms], dtype=torch.float64, device=device)
@@ -258,42 +281,32 @@ def engine_main(args):
   value = world * B * K / (total_ms * 1e-3)
 
   # ---- e2e: host actions in, scalars out, every step ---------------------------
+  # The public host-buffer call (BatchedEnvironment.step_host -> bsb_step_host): pinned actions H2D, the kernel,
+  # reward / discount / step_type D2H, one stream synchronise -- the agent reads the result before acting again.
   Ke = max(10, min(K, 200))
   host_actions = torch.randint(0, 2, (Ke, B), dtype=torch.int32).pin_memory()
-  host_out = {k: torch.empty(B, dtype=dt).pin_memory() for k, dt in
-              (('reward', torch.float32), ('discount', torch.float32), ('step_type', torch.int32))}
+  host_small = env.make_host_buffers(with_observation=False)
 
-  def e2e_loop(n, copy_obs, host_obs=None):
+  def e2e_loop(n, host):
     for t in range(n):
-      ts = env.step(host_actions[t % Ke], out=ring[t % RING])      # public API: H2D of the pinned actions inside
-      host_out['reward'].copy_(ts.reward, non_blocking=True)
-      host_out['discount'].copy_(ts.discount, non_blocking=True)
-      host_out['step_type'].copy_(ts.step_type, non_blocking=True)
-      if copy_obs:
-        host_obs.copy_(ts.observation, non_blocking=True)
-      torch.cuda.synchronize()                                      # the agent reads the result before acting again
+      env.step_host(host_actions[t % Ke], host, out=ring[t % RING])
 
-  e2e_loop(3, False)
-  if world > 1:
-    dist.barrier()
-  torch.cuda.synchronize()
-  t0 = time.perf_counter()
-  e2e_loop(Ke, False)
-  e2e_s = time.perf_counter() - t0
-  e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
-  if world > 1:
-    dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-  e2e_value = world * B * Ke / float(e2e_t[0])
+  def timed_e2e(n, host):
+    e2e_loop(3, host)
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e2e_loop(n, host)
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+    if world > 1:
+      dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    return world * B * n / float(dt[0])
+
+  e2e_value = timed_e2e(Ke, host_small)
   host_obs_value = None
   if not args.skip_host_obs:
-    host_obs = torch.empty((B, SIZE, SIZE), dtype=torch.float32).pin_memory()
-    e2e_loop(2, True, host_obs)
-    t0 = time.perf_counter()
-    e2e_loop(5, True, host_obs)
-    ho = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
-    if world > 1:
-      dist.all_reduce(ho, op=dist.ReduceOp.MAX)
-    host_obs_value = world * B * 5 / float(ho[0])
+    host_obs_value = timed_e2e(5, env.make_host_buffers(with_observation=True))
 
   if rank == 0:
     peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')

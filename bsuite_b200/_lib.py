@@ -26,8 +26,7 @@ WRAP_NONE, WRAP_REWARD_NOISE, WRAP_REWARD_SCALE = range(3)
 # enum bsb_rng_kind
 RNG_PHILOX, RNG_MT19937 = range(2)
 FLAG_TRACK_EPISODES = 1
-EPISODE_STAT_FIELDS = ('steps', 'episode', 'total_return', 'episode_len', 'episode_return',
-                       'last_episode_len', 'last_episode_return')
+EPISODE_STAT_FIELDS = ('steps', 'episode', 'total_return', 'episode_len', 'episode_return')
 
 
 class Config(ctypes.Structure):

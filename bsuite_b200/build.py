@@ -15,17 +15,20 @@ import time
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-SOURCES = [os.path.join(CSRC, 'bsb_engine.cu')]
-HEADERS = [os.path.join(CSRC, f) for f in ('bsb_rng.cuh', 'bsb_families.cuh', 'bsb_kernels.cuh')] + [
+FAMILIES = ('deep_sea', 'catch', 'cartpole', 'cartpole_swingup', 'mountain_car', 'memory_chain', 'bandit',
+            'umbrella_chain', 'discounting_chain', 'mnist')
+SOURCES = [os.path.join(CSRC, 'bsb_engine.cu')] + [os.path.join(CSRC, f'fam_{name}.cu') for name in FAMILIES]
+HEADERS = [os.path.join(CSRC, f) for f in ('bsb_rng.cuh', 'bsb_families.cuh', 'bsb_kernels.cuh', 'bsb_env.h',
+                                           'bsb_dispatch.cuh')] + [
     os.path.join(os.path.dirname(HERE), 'include', 'bsuite_b200.h')]
 OUTPUT = os.path.join(HERE, 'libbsuite_b200.so')
+OBJ_DIR = os.path.join(HERE, 'build')
 
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a',
     '-O3', '-std=c++17', '-lineinfo',
     '--fmad=false',                       # CPython/numpy never fuse a*b+c (float-dynamics parity)
     '-Xcompiler', '-fPIC,-ffp-contract=off,-O2',
-    '-shared',
 ]
 
 
@@ -36,26 +39,49 @@ def find_nvcc() -> str:
   raise RuntimeError('nvcc not found: bsuite_b200 needs the CUDA toolkit to build (no CPU-only build exists)')
 
 
-def is_stale() -> bool:
-  if not os.path.exists(OUTPUT):
+def _object_path(source: str) -> str:
+  return os.path.join(OBJ_DIR, os.path.basename(source)[:-3] + '.o')
+
+
+def _stale(target: str, deps) -> bool:
+  if not os.path.exists(target):
     return True
-  built = os.path.getmtime(OUTPUT)
-  return any(os.path.getmtime(p) > built for p in SOURCES + HEADERS)
+  built = os.path.getmtime(target)
+  return any(os.path.getmtime(p) > built for p in deps)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-  if not force and not is_stale():
-    return OUTPUT
-  cmd = [find_nvcc()] + NVCC_FLAGS + ['-o', OUTPUT] + SOURCES
+def is_stale() -> bool:
+  return _stale(OUTPUT, SOURCES + HEADERS)
+
+
+def _compile(nvcc: str, source: str, verbose: bool):
+  cmd = [nvcc] + NVCC_FLAGS + ['-c', source, '-o', _object_path(source)]
   if verbose:
     cmd += ['-Xptxas', '-v']
-  start = time.time()
   proc = subprocess.run(cmd, capture_output=True, text=True)
   if proc.returncode != 0:
     raise RuntimeError('nvcc failed:\n' + ' '.join(cmd) + '\n' + proc.stdout + proc.stderr)
-  if verbose:
-    sys.stderr.write(proc.stderr)
-  sys.stderr.write(f'[bsuite_b200.build] built {OUTPUT} in {time.time() - start:.1f}s\n')
+  return proc.stderr
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+  """Compiles every translation unit for sm_100a (in parallel) and links libbsuite_b200.so in-tree."""
+  import concurrent.futures
+  if not force and not is_stale():
+    return OUTPUT
+  nvcc = find_nvcc()
+  os.makedirs(OBJ_DIR, exist_ok=True)
+  start = time.time()
+  todo = [src for src in SOURCES if force or _stale(_object_path(src), [src] + HEADERS)]
+  with concurrent.futures.ThreadPoolExecutor(max_workers=min(len(todo) or 1, os.cpu_count() or 1)) as pool:
+    for log in pool.map(lambda src: _compile(nvcc, src, verbose), todo):
+      if verbose:
+        sys.stderr.write(log)
+  cmd = [nvcc, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', OUTPUT] + [_object_path(s) for s in SOURCES]
+  proc = subprocess.run(cmd, capture_output=True, text=True)
+  if proc.returncode != 0:
+    raise RuntimeError('link failed:\n' + ' '.join(cmd) + '\n' + proc.stdout + proc.stderr)
+  sys.stderr.write(f'[bsuite_b200.build] built {OUTPUT} ({len(todo)} translation units) in {time.time() - start:.1f}s\n')
   return OUTPUT
 
 

@@ -1,0 +1,164 @@
+// Host path and kernel launch, instantiated once per family (fam_<name>.cu).
+#pragma once
+#include "bsb_env.h"
+
+namespace bsb {
+
+// --------------------------- host path --------------------------------------
+template <class F> struct HostEmit {
+  template <class R> static void run(const EnvParams& p, const typename F::Lane& L, R&, float* dst) { F::row(p, L, dst, 1); }
+};
+template <> struct HostEmit<UmbrellaChain> {
+  template <class R> static void run(const EnvParams& p, const UmbrellaChain::Lane& L, R& r, float* dst) { UmbrellaChain::row(p, L, r, dst, 1); }
+};
+template <> struct HostEmit<DeepSea> {
+  template <class R> static void run(const EnvParams& p, const DeepSea::Lane& L, R&, float* dst) {
+    for (int e = 0; e < p.obs_numel; ++e) dst[e] = 0.f;
+    if (L.hot >= 0) dst[L.hot] = 1.f;
+  }
+};
+template <> struct HostEmit<Catch> {
+  template <class R> static void run(const EnvParams& p, const Catch::Lane& L, R&, float* dst) {
+    for (int e = 0; e < p.obs_numel; ++e) dst[e] = 0.f;
+    dst[L.hot_a] = 1.f; dst[L.hot_b] = 1.f;
+  }
+};
+template <> struct HostEmit<Mnist> {
+  template <class R> static void run(const EnvParams& p, const Mnist::Lane& L, R&, float* dst) {
+    if (L.image < 0) { for (int e = 0; e < p.obs_numel; ++e) dst[e] = 0.f; return; }
+    const int8_t* src = p.images + (int64_t)L.image * p.obs_numel;
+    for (int e = 0; e < p.obs_numel; ++e) dst[e] = Mnist::pixel(src[e]);
+  }
+};
+
+template <class F, int RK>
+void host_run(const EnvParams& p, const LaunchArgs& a) {
+  typedef typename RngOf<RK>::type R;
+  const int64_t B = p.batch;
+  const int K = p.obs_numel;
+  const bool noise = p.wrapper == BSB_WRAP_REWARD_NOISE;
+  const bool has_rng = p.rng_pos != nullptr;
+  const bool track = p.ep != nullptr;
+  for (int64_t lane = 0; lane < B; ++lane) {
+    typename F::Lane L;
+    R rng, wrng;
+    EpisodeStats ep;
+    ActionStream action_stream;
+    action_stream.open();
+    if (a.mode == MODE_INIT) F::init(p, L); else F::load(p, lane, L);
+    if (has_rng) rng_open(rng, p, lane, false);
+    if (noise) rng_open(wrng, p, lane, true);
+    if (track) ep.load(p, lane);
+    if (a.mode == MODE_INIT) {
+      F::ctor_draws(p, L, rng);
+      F::store(p, lane, L);
+      if (has_rng) rng_close(rng, p, lane, false);
+      continue;
+    }
+    for (int64_t t = 0; t < a.T; ++t) {
+      const int64_t off = t * B + lane;
+      int32_t action = 0;
+      if (a.mode == MODE_STEP) {
+        action = a.actions ? a.actions[off]
+                           : action_stream.sample(a.action_seed, p.lane_offset + (uint64_t)lane, (uint64_t)(a.step0 + t), p.num_actions);
+        if (a.actions_out) a.actions_out[off] = action;
+      }
+      const StepOut o = lane_transition<F, R, R>(p, lane, L, rng, wrng, action, a.mode, noise);
+      if (track) ep.track(o);
+      if (a.reward) a.reward[off] = (float)o.reward;
+      if (a.reward_f64) a.reward_f64[off] = o.reward;
+      if (a.discount) a.discount[off] = o.discount;
+      if (a.step_type) a.step_type[off] = o.step_type;
+      HostEmit<F>::run(p, L, rng, a.obs + off * (int64_t)K);
+    }
+    F::store(p, lane, L);
+    if (has_rng) rng_close(rng, p, lane, false);
+    if (noise) rng_close(wrng, p, lane, true);
+    if (track) ep.store(p, lane);
+  }
+}
+
+// --------------------------- device dispatch --------------------------------
+template <class F, int RK, bool kNoise, bool kTrack>
+int device_launch(bsb_env* e, LaunchArgs a, cudaStream_t stream) {
+  const int K = e->p.obs_numel;
+  const bool is_onehot = EmitKind<F>::value == EMIT_ONEHOT;
+  const int64_t B = e->p.batch;
+  a.emit_bulk = is_onehot ? e->deep_sea_bulk : e->emit_bulk;
+  a.group_lanes = 1;
+  a.work_counter = nullptr;
+  a.work_base = 0;
+  int threads = e->block_threads;
+  bool persistent = false;
+  if (is_onehot && a.emit_bulk) {
+    // Lanes per bulk store: the largest power of two <= 16 with one store <= 40 KB (BSB_DEEP_SEA_GROUP overrides).
+    // Measured on B200 (tools/bench_variants.py): N = 32 -> 8 lanes (32 KB stores), N = 50 -> 4 lanes (40 KB).
+    const size_t tile = (size_t)K * 4;
+    int m = 1;
+    while (m < 16 && (size_t)(2 * m) * tile <= 40 * 1024) m <<= 1;
+    if (e->deep_sea_group > 0) m = e->deep_sea_group;
+    if (((size_t)m * tile) % 16 != 0 || (size_t)TILE_STAGES * m * tile > 100 * 1024) {
+      a.emit_bulk = 0;                      // tiles too large (or misaligned) for the staged path: vector stores
+    } else {
+      a.group_lanes = m; threads = 32; persistent = e->deep_sea_persistent != 0;
+    }
+  }
+  a.use_pdl = (e->use_pdl && a.mode == MODE_STEP && a.T == 1) ? 1 : 0;
+  const size_t per_warp = smem_floats_per_warp<F>(K, a.emit_bulk != 0, a.group_lanes) * sizeof(float);
+  size_t smem = per_warp * (size_t)(threads / 32);
+  while (smem > 96 * 1024 && threads > 32) { threads >>= 1; smem = per_warp * (size_t)(threads / 32); }
+  if (smem > 200 * 1024) return fail(BSB_UNSUPPORTED, "observation too large for the staged emitter");
+  auto kernel = transition_kernel<F, RK, kNoise, kTrack>;
+  if (smem > 48 * 1024) BSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int64_t grid = (B + threads - 1) / threads;
+  if (persistent) {
+    // As many CTAs as are co-resident (shared-memory bound; 1 KB per CTA is reserved by the driver); each warp
+    // then owns a contiguous, equally sized range of lanes.
+    const int64_t per_sm = (int64_t)((227 * 1024) / (smem + 1024));
+    const int64_t resident = (int64_t)e->num_sms * (per_sm < 1 ? 1 : (per_sm > 16 ? 16 : per_sm));
+    if (grid > resident) {
+      grid = resident;
+      a.work_counter = e->work_counter;
+      a.work_base = e->work_base;
+    } else {
+      persistent = false;      // everything is resident anyway: one chunk per warp
+    }
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  if (a.use_pdl) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  BSB_CUDA(cudaLaunchKernelEx(&cfg, kernel, e->p, a));
+  if (a.work_counter) e->work_base += (unsigned long long)((B + 31) / 32) + (unsigned long long)grid * (unsigned long long)(threads / 32);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return BSB_OK;
+}
+
+template <class F, int RK>
+int device_launch_flags(bsb_env* e, const LaunchArgs& a, cudaStream_t stream) {
+  const bool noise = e->p.wrapper == BSB_WRAP_REWARD_NOISE && a.mode != MODE_INIT;
+  const bool track = e->p.ep != nullptr && a.mode != MODE_INIT;
+  if (noise) return track ? device_launch<F, RK, true, true>(e, a, stream) : device_launch<F, RK, true, false>(e, a, stream);
+  return track ? device_launch<F, RK, false, true>(e, a, stream) : device_launch<F, RK, false, false>(e, a, stream);
+}
+
+template <class F>
+int run_family(bsb_env* e, const LaunchArgs& a, cudaStream_t stream) {
+  const bool mt = e->p.rng_kind == BSB_RNG_MT19937;
+  if (e->device < 0) {
+    if (mt) host_run<F, 1>(e->p, a); else host_run<F, 0>(e->p, a);
+    return BSB_OK;
+  }
+  return mt ? device_launch_flags<F, 1>(e, a, stream) : device_launch_flags<F, 0>(e, a, stream);
+}
+
+}  // namespace bsb

@@ -4,37 +4,22 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a --fmad=false -lineinfo ...
 // (--fmad=false: CPython/numpy never contract a*b+c; the float-dynamics
 // families must evaluate the reference's expressions operation by operation.)
-#include <cuda_runtime.h>
-
-#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <string>
-#include <utility>
-#include <vector>
 
-#include "../../include/bsuite_b200.h"
-#include "bsb_kernels.cuh"
+#include "bsb_env.h"
 
 using namespace bsb;
 
-namespace {
-
-thread_local std::string g_last_error;
+namespace bsb {
 std::atomic<int64_t> g_launches{0};
-
+namespace { thread_local std::string g_last_error; }
 int fail(int code, const std::string& msg) { g_last_error = msg; return code; }
+const char* last_error_cstr() { return g_last_error.c_str(); }
+}  // namespace bsb
 
-#define BSB_CUDA(expr)                                                                   \
-  do {                                                                                   \
-    cudaError_t e__ = (expr);                                                            \
-    if (e__ != cudaSuccess)                                                              \
-      return fail(e__ == cudaErrorMemoryAllocation ? BSB_OUT_OF_MEMORY : BSB_CUDA_ERROR, \
-                  std::string(#expr) + ": " + cudaGetErrorString(e__));                  \
-  } while (0)
-
-struct InfoNames { int n; const char* names[BSB_MAX_INFO]; };
+namespace {
 
 InfoNames info_names(int family) {
   switch (family) {
@@ -53,18 +38,6 @@ InfoNames info_names(int family) {
 }
 
 }  // namespace
-
-struct bsb_env {
-  EnvParams p;
-  int device;             // BSB_DEVICE_HOST or CUDA ordinal
-  int64_t steps_done;
-  InfoNames names;
-  std::vector<void*> allocs;
-  std::vector<std::pair<void*, size_t> > state_blocks;  // snapshot layout
-  // bsb_step_host scratch (device)
-  int32_t* h2d_actions; float* d_reward; double* d_reward64; float* d_discount; int32_t* d_step_type; float* d_obs;
-  cudaStream_t copy_stream;
-};
 
 namespace {
 
@@ -104,124 +77,19 @@ template <class T> int env_alloc_t(bsb_env* e, T** out, size_t count, bool snaps
   return rc;
 }
 
-// --------------------------- host path --------------------------------------
-template <class F> struct HostEmit {
-  template <class R> static void run(const EnvParams& p, const typename F::Lane& L, R&, float* dst) { F::row(p, L, dst, 1); }
-};
-template <> struct HostEmit<UmbrellaChain> {
-  template <class R> static void run(const EnvParams& p, const UmbrellaChain::Lane& L, R& r, float* dst) { UmbrellaChain::row(p, L, r, dst, 1); }
-};
-template <> struct HostEmit<DeepSea> {
-  template <class R> static void run(const EnvParams& p, const DeepSea::Lane& L, R&, float* dst) {
-    for (int e = 0; e < p.obs_numel; ++e) dst[e] = 0.f;
-    if (L.hot >= 0) dst[L.hot] = 1.f;
-  }
-};
-template <> struct HostEmit<Catch> {
-  template <class R> static void run(const EnvParams& p, const Catch::Lane& L, R&, float* dst) {
-    for (int e = 0; e < p.obs_numel; ++e) dst[e] = 0.f;
-    dst[L.hot_a] = 1.f; dst[L.hot_b] = 1.f;
-  }
-};
-template <> struct HostEmit<Mnist> {
-  template <class R> static void run(const EnvParams& p, const Mnist::Lane& L, R&, float* dst) {
-    if (L.image < 0) { for (int e = 0; e < p.obs_numel; ++e) dst[e] = 0.f; return; }
-    const int8_t* src = p.images + (int64_t)L.image * p.obs_numel;
-    for (int e = 0; e < p.obs_numel; ++e) dst[e] = Mnist::pixel(src[e]);
-  }
-};
-
-template <class F, int RK>
-void host_run(const EnvParams& p, const LaunchArgs& a) {
-  typedef typename RngOf<RK>::type R;
-  const int64_t B = p.batch;
-  const int K = p.obs_numel;
-  const bool noise = p.wrapper == BSB_WRAP_REWARD_NOISE;
-  const bool has_rng = p.rng_pos != nullptr;
-  const bool track = p.ep != nullptr;
-  for (int64_t lane = 0; lane < B; ++lane) {
-    typename F::Lane L;
-    R rng, wrng;
-    EpisodeStats ep;
-    if (a.mode == MODE_INIT) F::init(p, L); else F::load(p, lane, L);
-    if (has_rng) rng_open(rng, p, lane, false);
-    if (noise) rng_open(wrng, p, lane, true);
-    if (track) ep.load(p, lane);
-    if (a.mode == MODE_INIT) {
-      F::ctor_draws(p, L, rng);
-      F::store(p, lane, L);
-      if (has_rng) rng_close(rng, p, lane, false);
-      continue;
-    }
-    for (int64_t t = 0; t < a.T; ++t) {
-      const int64_t off = t * B + lane;
-      int32_t action = 0;
-      if (a.mode == MODE_STEP) {
-        action = a.actions ? a.actions[off]
-                           : sample_action(a.action_seed, p.lane_offset + (uint64_t)lane, (uint64_t)(a.step0 + t), p.num_actions);
-        if (a.actions_out) a.actions_out[off] = action;
-      }
-      const StepOut o = lane_transition<F, R, R>(p, lane, L, rng, wrng, action, a.mode, noise);
-      if (track) ep.track(o);
-      if (a.reward) a.reward[off] = (float)o.reward;
-      if (a.reward_f64) a.reward_f64[off] = o.reward;
-      if (a.discount) a.discount[off] = o.discount;
-      if (a.step_type) a.step_type[off] = o.step_type;
-      HostEmit<F>::run(p, L, rng, a.obs + off * (int64_t)K);
-    }
-    F::store(p, lane, L);
-    if (has_rng) rng_close(rng, p, lane, false);
-    if (noise) rng_close(wrng, p, lane, true);
-    if (track) ep.store(p, lane);
-  }
-}
-
-// --------------------------- device dispatch --------------------------------
-template <class F, int RK, bool kNoise>
-int device_launch(const bsb_env* e, const LaunchArgs& a, cudaStream_t stream) {
-  const int K = e->p.obs_numel;
-  int threads = 128;
-  size_t smem = 0;
-  if (EmitKind<F>::value == EMIT_ROWS) {
-    smem = (size_t)(threads / 32) * 32 * (size_t)K * sizeof(float);
-    while (smem > 96 * 1024 && threads > 32) { threads >>= 1; smem = (size_t)(threads / 32) * 32 * (size_t)K * sizeof(float); }
-    if (smem > 200 * 1024) return fail(BSB_UNSUPPORTED, "observation row too long for the staged emitter");
-    if (smem > 48 * 1024)
-      BSB_CUDA(cudaFuncSetAttribute(transition_kernel<F, RK, kNoise>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  }
-  const int64_t B = e->p.batch;
-  const unsigned grid = (unsigned)((B + threads - 1) / threads);
-  transition_kernel<F, RK, kNoise><<<grid, threads, smem, stream>>>(e->p, a);
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  BSB_CUDA(cudaGetLastError());
-  return BSB_OK;
-}
-
-template <class F>
-int run_family(bsb_env* e, const LaunchArgs& a, cudaStream_t stream) {
-  const bool mt = e->p.rng_kind == BSB_RNG_MT19937;
-  if (e->device < 0) {
-    if (mt) host_run<F, 1>(e->p, a); else host_run<F, 0>(e->p, a);
-    return BSB_OK;
-  }
-  const bool noise = e->p.wrapper == BSB_WRAP_REWARD_NOISE && a.mode != MODE_INIT;
-  if (mt) return noise ? device_launch<F, 1, true>(e, a, stream) : device_launch<F, 1, false>(e, a, stream);
-  return noise ? device_launch<F, 0, true>(e, a, stream) : device_launch<F, 0, false>(e, a, stream);
-}
-
 int run(bsb_env* e, const LaunchArgs& a, cudaStream_t stream) {
   DeviceGuard guard(e->device);
   switch (e->p.family) {
-    case BSB_DEEP_SEA: return run_family<DeepSea>(e, a, stream);
-    case BSB_CATCH: return run_family<Catch>(e, a, stream);
-    case BSB_CARTPOLE: return run_family<Cartpole>(e, a, stream);
-    case BSB_CARTPOLE_SWINGUP: return run_family<CartpoleSwingup>(e, a, stream);
-    case BSB_MOUNTAIN_CAR: return run_family<MountainCar>(e, a, stream);
-    case BSB_MEMORY_CHAIN: return run_family<MemoryChain>(e, a, stream);
-    case BSB_BANDIT: return run_family<Bandit>(e, a, stream);
-    case BSB_UMBRELLA_CHAIN: return run_family<UmbrellaChain>(e, a, stream);
-    case BSB_DISCOUNTING_CHAIN: return run_family<DiscountingChain>(e, a, stream);
-    case BSB_MNIST: return run_family<Mnist>(e, a, stream);
+    case BSB_DEEP_SEA: return run_deep_sea(e, a, stream);
+    case BSB_CATCH: return run_catch(e, a, stream);
+    case BSB_CARTPOLE: return run_cartpole(e, a, stream);
+    case BSB_CARTPOLE_SWINGUP: return run_cartpole_swingup(e, a, stream);
+    case BSB_MOUNTAIN_CAR: return run_mountain_car(e, a, stream);
+    case BSB_MEMORY_CHAIN: return run_memory_chain(e, a, stream);
+    case BSB_BANDIT: return run_bandit(e, a, stream);
+    case BSB_UMBRELLA_CHAIN: return run_umbrella_chain(e, a, stream);
+    case BSB_DISCOUNTING_CHAIN: return run_discounting_chain(e, a, stream);
+    case BSB_MNIST: return run_mnist(e, a, stream);
   }
   return fail(BSB_INVALID_ARGUMENT, "unknown family");
 }
@@ -309,7 +177,7 @@ void destroy_env(bsb_env* e) {
 extern "C" {
 
 int32_t bsb_abi_version(void) { return BSB_ABI_VERSION; }
-const char* bsb_last_error(void) { return g_last_error.c_str(); }
+const char* bsb_last_error(void) { return bsb::last_error_cstr(); }
 int64_t bsb_launch_count(void) { return g_launches.load(); }
 
 int32_t bsb_create(const bsb_config* config, int64_t batch, int32_t device, uint64_t seed, uint64_t lane_offset, bsb_env** out) {
@@ -333,6 +201,21 @@ int32_t bsb_create(const bsb_config* config, int64_t batch, int32_t device, uint
   bsb_env* e = new bsb_env();
   memset(&e->p, 0, sizeof(e->p));
   e->device = device; e->steps_done = 0; e->names = info_names(c.family);
+  {  // tuning knobs (environment variables, read once per handle)
+    auto flag = [](const char* name, int dflt) { const char* v = getenv(name); return v ? (atoi(v) != 0 ? 1 : 0) : dflt; };
+    const char* bt = getenv("BSB_BLOCK_THREADS");
+    e->block_threads = bt ? atoi(bt) : 64;
+    if (e->block_threads != 32 && e->block_threads != 64 && e->block_threads != 128) e->block_threads = 64;
+    e->emit_bulk = flag("BSB_EMIT_BULK", 1);
+    e->deep_sea_bulk = flag("BSB_DEEP_SEA_BULK", 1);
+    { const char* g = getenv("BSB_DEEP_SEA_GROUP"); e->deep_sea_group = g ? atoi(g) : 0;
+      if (e->deep_sea_group < 0 || e->deep_sea_group > 32 || (e->deep_sea_group & (e->deep_sea_group - 1))) e->deep_sea_group = 0; }
+    e->use_pdl = flag("BSB_PDL", 1);
+    e->deep_sea_persistent = flag("BSB_DEEP_SEA_PERSISTENT", 1);
+    e->work_counter = nullptr; e->work_base = 0;
+    e->num_sms = 148;
+    if (device >= 0) { int n = 0; if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && n > 0) e->num_sms = n; }
+  }
   e->h2d_actions = nullptr; e->d_reward = nullptr; e->d_reward64 = nullptr; e->d_discount = nullptr; e->d_step_type = nullptr; e->d_obs = nullptr;
   e->copy_stream = nullptr;
   DeviceGuard guard(device);
@@ -380,13 +263,14 @@ int32_t bsb_create(const bsb_config* config, int64_t batch, int32_t device, uint
     BSB_TRY(env_upload(e, l, c.table2, (size_t)c.table2_bytes));
     p.images = d; p.labels = l;
   }
+  if (device >= 0) BSB_TRY(env_alloc_t(e, &e->work_counter, 1, false));
   // lane state
   BSB_TRY(env_alloc_t(e, &p.st_word, B, true));
   if (c.family == BSB_MEMORY_CHAIN) BSB_TRY(env_alloc_t(e, &p.st_ctx, B, true));
   if (c.family == BSB_CARTPOLE || c.family == BSB_CARTPOLE_SWINGUP) BSB_TRY(env_alloc_t(e, &p.st_f64, 6 * B, true));
   if (c.family == BSB_MOUNTAIN_CAR) BSB_TRY(env_alloc_t(e, &p.st_f64, 2 * B, true));
   BSB_TRY(env_alloc_t(e, &p.info, (size_t)BSB_MAX_INFO * B, true));
-  if (c.flags & BSB_FLAG_TRACK_EPISODES) BSB_TRY(env_alloc_t(e, &p.ep, 7 * B, true));
+  if (c.flags & BSB_FLAG_TRACK_EPISODES) BSB_TRY(env_alloc_t(e, &p.ep, 5 * B, true));
   // RNG state
   const bool env_rng = family_uses_env_rng(c);
   const bool noise = c.wrapper == BSB_WRAP_REWARD_NOISE;
@@ -513,7 +397,7 @@ int32_t bsb_read_info(bsb_env* env, int32_t index, double* dst, void* stream) {
 int32_t bsb_read_episode_stats(bsb_env* env, int32_t field, double* dst, void* stream) {
   if (!env || !dst) return fail(BSB_INVALID_ARGUMENT, "null argument");
   if (!env->p.ep) return fail(BSB_INVALID_ARGUMENT, "environment was created without BSB_FLAG_TRACK_EPISODES");
-  if (field < 0 || field >= 7) return fail(BSB_INVALID_ARGUMENT, "episode-stat field out of range");
+  if (field < 0 || field >= 5) return fail(BSB_INVALID_ARGUMENT, "episode-stat field out of range");
   return copy_field(env, env->p.ep + (size_t)field * (size_t)env->p.batch, dst, stream);
 }
 

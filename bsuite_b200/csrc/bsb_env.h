@@ -1,0 +1,65 @@
+// Internal declarations shared by the engine and the per-family translation units.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/bsuite_b200.h"
+#include "bsb_kernels.cuh"
+
+namespace bsb {
+
+struct InfoNames { int n; const char* names[BSB_MAX_INFO]; };
+
+int fail(int code, const std::string& msg);           // records the thread-local error string
+const char* last_error_cstr();
+extern std::atomic<int64_t> g_launches;                // kernels launched by this library
+
+#define BSB_CUDA(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t e__ = (expr);                                                            \
+    if (e__ != cudaSuccess)                                                              \
+      return ::bsb::fail(e__ == cudaErrorMemoryAllocation ? BSB_OUT_OF_MEMORY : BSB_CUDA_ERROR, \
+                         std::string(#expr) + ": " + cudaGetErrorString(e__));           \
+  } while (0)
+
+}  // namespace bsb
+
+struct bsb_env {
+  bsb::EnvParams p;
+  int device;             // BSB_DEVICE_HOST or CUDA ordinal
+  int64_t steps_done;
+  // tuning knobs (environment variables, read once per handle)
+  int block_threads;      // CTA size of the transition kernel (32 / 64 / 128)
+  int emit_bulk;          // TMA bulk stores for the row / board emitters
+  int deep_sea_bulk;      // TMA bulk stores for deep_sea tiles (else 16-byte streaming stores)
+  int deep_sea_group;     // lanes per deep_sea bulk store (0 = automatic)
+  int deep_sea_persistent; // persistent grid + dynamic chunk dealing for the deep_sea bulk path
+  unsigned long long* work_counter;  // device counter of the dynamic chunk scheduler
+  unsigned long long work_base;      // its value when the next launch starts
+  int use_pdl;            // programmatic dependent launch between consecutive steps
+  int num_sms;
+  bsb::InfoNames names;
+  std::vector<void*> allocs;
+  std::vector<std::pair<void*, size_t> > state_blocks;  // snapshot layout
+  // bsb_step_host scratch (device)
+  int32_t* h2d_actions; float* d_reward; double* d_reward64; float* d_discount; int32_t* d_step_type; float* d_obs;
+  cudaStream_t copy_stream;
+};
+
+namespace bsb {
+// One entry per family, each defined in its own translation unit (fam_<name>.cu).
+int run_deep_sea(bsb_env*, const LaunchArgs&, cudaStream_t);
+int run_catch(bsb_env*, const LaunchArgs&, cudaStream_t);
+int run_cartpole(bsb_env*, const LaunchArgs&, cudaStream_t);
+int run_cartpole_swingup(bsb_env*, const LaunchArgs&, cudaStream_t);
+int run_mountain_car(bsb_env*, const LaunchArgs&, cudaStream_t);
+int run_memory_chain(bsb_env*, const LaunchArgs&, cudaStream_t);
+int run_bandit(bsb_env*, const LaunchArgs&, cudaStream_t);
+int run_umbrella_chain(bsb_env*, const LaunchArgs&, cudaStream_t);
+int run_discounting_chain(bsb_env*, const LaunchArgs&, cudaStream_t);
+int run_mnist(bsb_env*, const LaunchArgs&, cudaStream_t);
+}  // namespace bsb

@@ -51,7 +51,7 @@ struct EnvParams {
   uint64_t* st_ctx;    // [B]   memory_chain context bits
   double* st_f64;      // [6][B] float64 dynamics state (+ episode_return)
   double* info;        // [BSB_MAX_INFO][B] bsuite_info() accumulators
-  double* ep;          // [7][B] Logging accumulators, or null
+  double* ep;          // [5][B] Logging accumulators, or null
   // RNG state: env stream and reward-wrapper stream
   uint64_t* rng_pos;  double* rng_gauss;
   uint64_t* wrng_pos; double* wrng_gauss;
@@ -87,6 +87,7 @@ BSB_HD double square_like_reference(double x) {
 // deep_sea  (environments/deep_sea.py)
 // ===========================================================================
 struct DeepSea {
+  static const bool kIsDeepSea = true;
   struct Lane { uint32_t row, col, bad, nr; int32_t hot; };
   enum { kInfo = 2 };  // total_bad_episodes, denoised_return  (deep_sea.py:153-155)
 
@@ -146,6 +147,7 @@ struct DeepSea {
 // catch  (environments/catch.py)
 // ===========================================================================
 struct Catch {
+  static const bool kIsDeepSea = false;
   struct Lane { uint32_t ball_x, ball_y, paddle_x, nr; int32_t hot_a, hot_b; };
   enum { kInfo = 1 };  // total_regret (catch.py:116-117)
 
@@ -213,6 +215,7 @@ BSB_HD PoleState advance_pole(const EnvParams& p, const PoleState& s, int32_t ac
 
 template <bool kSwingup>
 struct CartpoleT {
+  static const bool kIsDeepSea = false;
   // obs: 6 (cartpole.py:167-177) or 8 (cartpole_swingup.py:137-150) floats
   enum { kObs = kSwingup ? 8 : 6, kInfo = kSwingup ? 3 : 2 };
   struct Lane { PoleState s; double episode_return, raw_return; uint32_t nr; };
@@ -296,6 +299,7 @@ typedef CartpoleT<true> CartpoleSwingup;
 // mountain_car  (environments/mountain_car.py)
 // ===========================================================================
 struct MountainCar {
+  static const bool kIsDeepSea = false;
   enum { kObs = 3, kInfo = 1 };  // raw_return (mountain_car.py:101-102)
   struct Lane { double pos, vel, raw_return; uint32_t t, nr; };
 
@@ -337,6 +341,7 @@ struct MountainCar {
 // memory_chain  (environments/memory_chain.py)
 // ===========================================================================
 struct MemoryChain {
+  static const bool kIsDeepSea = false;
   enum { kInfo = 2 };  // total_perfect, total_regret (memory_chain.py:108-111)
   struct Lane { uint32_t t, query, nr, obs_t; uint64_t ctx; };
 
@@ -384,6 +389,7 @@ struct MemoryChain {
 // bandit  (environments/bandit.py)
 // ===========================================================================
 struct Bandit {
+  static const bool kIsDeepSea = false;
   enum { kObs = 1, kInfo = 1 };  // total_regret
   struct Lane { uint32_t nr; };
   static BSB_HD void load(const EnvParams& p, int64_t i, Lane& L) { L.nr = p.st_word[i] >> 31; }
@@ -403,6 +409,7 @@ struct Bandit {
 // umbrella_chain  (environments/umbrella_chain.py)
 // ===========================================================================
 struct UmbrellaChain {
+  static const bool kIsDeepSea = false;
   enum { kInfo = 1 };  // total_regret
   struct Lane { uint32_t t, need, has, nr; };
   static BSB_HD void load(const EnvParams& p, int64_t i, Lane& L) {
@@ -442,6 +449,7 @@ struct UmbrellaChain {
 // discounting_chain  (environments/discounting_chain.py)
 // ===========================================================================
 struct DiscountingChain {
+  static const bool kIsDeepSea = false;
   enum { kObs = 2, kInfo = 0 };  // bsuite_info() == {}
   struct Lane { uint32_t t, nr; int32_t context; };
   static BSB_HD void load(const EnvParams& p, int64_t i, Lane& L) {
@@ -475,6 +483,7 @@ struct DiscountingChain {
 // mnist  (environments/mnist.py)
 // ===========================================================================
 struct Mnist {
+  static const bool kIsDeepSea = false;
   enum { kInfo = 1 };  // total_regret
   struct Lane { uint32_t label, nr; int32_t image; };
   static BSB_HD void load(const EnvParams& p, int64_t i, Lane& L) {
@@ -499,36 +508,28 @@ struct Mnist {
   static BSB_HD float pixel(int8_t v) { return (float)v / 255.0f; }
 };
 
-// ===========================================================================
-// Reward wrappers (utils/wrappers.py:275-283, 338-346): applied to every
-// non-FIRST timestep; bsuite_info() stays un-noised / un-scaled (:305-306).
-// ===========================================================================
-template <class WR>
-BSB_HD void apply_reward_wrapper(const EnvParams& p, StepOut& o, WR& wrng) {
-  if (o.step_type == FIRST) return;
-  if (p.wrapper == 1) o.reward = o.reward + p.noise_scale * wrng.randn();
-  else if (p.wrapper == 2) o.reward = o.reward * p.reward_scale;
-}
-
-// Logging-wrapper bookkeeping (utils/wrappers.py:85-110) on the wrapped reward.
+// Logging-wrapper bookkeeping (utils/wrappers.py:85-110) on the wrapped reward, five float64 columns per
+// lane: steps, episode, total_return, episode_len, episode_return.  The reference zeroes episode_len /
+// episode_return right after it has logged a LAST timestep; here they are zeroed when the NEXT episode starts
+// (on FIRST), so at a LAST timestep -- the moment the reference writes its row (:99-101) -- and until the lane
+// steps again they hold the finished episode's values, with no extra "last episode" columns to carry.
 struct EpisodeStats {
-  double steps, episode, total_return, episode_len, episode_return, last_len, last_return;
+  double steps, episode, total_return, episode_len, episode_return;
   BSB_HD void load(const EnvParams& p, int64_t i) {
     const int64_t B = p.batch;
     steps = p.ep[i]; episode = p.ep[B + i]; total_return = p.ep[2 * B + i]; episode_len = p.ep[3 * B + i];
-    episode_return = p.ep[4 * B + i]; last_len = p.ep[5 * B + i]; last_return = p.ep[6 * B + i];
+    episode_return = p.ep[4 * B + i];
   }
   BSB_HD void store(const EnvParams& p, int64_t i) const {
     const int64_t B = p.batch;
     p.ep[i] = steps; p.ep[B + i] = episode; p.ep[2 * B + i] = total_return; p.ep[3 * B + i] = episode_len;
-    p.ep[4 * B + i] = episode_return; p.ep[5 * B + i] = last_len; p.ep[6 * B + i] = last_return;
+    p.ep[4 * B + i] = episode_return;
   }
   BSB_HD void track(const StepOut& o) {
-    if (o.step_type != FIRST) { steps += 1.0; episode_len += 1.0; }
+    if (o.step_type == FIRST) { episode_len = 0.0; episode_return = 0.0; return; }
+    steps += 1.0; episode_len += 1.0;
+    episode_return += o.reward; total_return += o.reward;
     if (o.step_type == LAST) episode += 1.0;
-    const double r = (o.step_type == FIRST) ? 0.0 : o.reward;
-    episode_return += r; total_return += r;
-    if (o.step_type == LAST) { last_len = episode_len; last_return = episode_return; episode_len = 0.0; episode_return = 0.0; }
   }
 };
 

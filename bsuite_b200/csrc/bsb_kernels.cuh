@@ -1,24 +1,33 @@
-// Fused transition kernels: one per environment family (template F), each
-// specialised on the bit source (Philox / MT19937) and on whether the
-// RewardNoise wrapper stream is live.
+// Fused transition kernels: one per environment family (template F), specialised
+// on the bit source (Philox / MT19937), on whether the RewardNoise wrapper stream
+// is live, and on whether the Logging accumulators are tracked.
 //
 // Thread = lane for the scalar transition (state word(s), action, reward,
-// discount, step_type are all coalesced 4/8-byte accesses).  Observations are
-// dense float32 tensors that must be written fresh every step (the reference
-// allocates a new array per step: deep_sea.py:104, catch.py:114), and they are
-// the HBM traffic that bounds the kernel, so they are emitted WARP-
-// COOPERATIVELY with 16-byte streaming stores:
-//   * tile families (deep_sea N x N one-hot, mnist 28 x 28): the warp walks its
-//     32 lanes; for each lane all 32 threads write that lane's contiguous tile,
-//     the hot cell (or the gathered image) decided per float4 from a descriptor
-//     broadcast with __shfl_sync.
-//   * catch: the warp's 32 boards are one contiguous span; each float4 is
-//     rendered from the (ball, paddle) cells of the lane(s) it overlaps.
+// discount, step_type are coalesced 4/8-byte accesses).  Observations are dense
+// float32 tensors that must be written fresh every step (the reference allocates
+// a new array per step: deep_sea.py:104, catch.py:114); they are the HBM traffic
+// that bounds the kernel and are emitted WARP-COOPERATIVELY:
+//
 //   * row families ((1,k) vectors): each thread renders its row into a per-warp
-//     shared-memory stage, the warp then streams the contiguous [32, k] block.
-// A launch covers T consecutive steps with lane state held in registers
-// (T = 1 for bsb_step); actions come from the caller or from the on-device
-// Philox action stream.
+//     shared-memory stage (double buffered); the warp's [32, k] block is
+//     contiguous in global memory, so one elected lane sends it with a single TMA
+//     bulk store (cp.async.bulk shared::cta -> global).
+//   * catch: the same stage holds the warp's 32 boards and stays ZERO between
+//     steps; each thread only un-pokes its two old cells and pokes its two new
+//     ones before the elected lane issues the bulk store of all 32 boards.
+//   * deep_sea (N x N one-hot tile per lane, 4 KB at N = 32): default path is
+//     16-byte streaming stores -- the warp walks its 32 lanes and all threads write
+//     each lane's contiguous tile, the hot cell chosen per float4 from a descriptor
+//     broadcast by __shfl_sync.  Alternative path (emit_bulk): a per-warp ring of 4
+//     zeroed tiles in shared memory; the elected lane pokes the hot cell of the next
+//     free tile and issues one bulk store per lane tile.
+//   * mnist: gathered int8 image -> float32 tile, 16-byte stores.
+//
+// A launch covers T consecutive steps with lane state held in registers (T = 1
+// for bsb_step); actions come from the caller or from the on-device Philox
+// action stream.  With use_pdl the kernel is launched with programmatic stream
+// serialization: everything before griddepcontrol.wait (index math, zeroing the
+// shared-memory stages) overlaps the tail of the previous step's kernel.
 #pragma once
 #include "bsb_families.cuh"
 
@@ -37,6 +46,12 @@ struct LaunchArgs {
   uint64_t action_seed;
   int32_t mode;             // 0 = step, 1 = reset every lane, 2 = constructor init
   int32_t obs_vec_ok;       // obs base and per-step stride are 16-byte aligned
+  int32_t emit_bulk;        // use TMA bulk stores where the emitter supports them
+  int32_t use_pdl;          // launched with programmatic stream serialization
+  int32_t group_lanes;      // deep_sea bulk path: lanes per bulk store (power of two, 1..32)
+  int32_t reserved;
+  unsigned long long* work_counter;  // persistent launches: monotonically increasing chunk counter (device)
+  unsigned long long work_base;      // value of *work_counter at which this launch's chunk 0 starts
 };
 
 enum { MODE_STEP = 0, MODE_RESET = 1, MODE_INIT = 2 };
@@ -76,6 +91,8 @@ BSB_HD void rng_close(const LegacyRng<MtSrc>& r, const EnvParams& p, int64_t i, 
 }
 
 // ----- the per-lane call sequence of base.Environment.step (base.py:59-65) --
+// followed by the reward wrappers (utils/wrappers.py:275-283, 338-346), which
+// act on every non-FIRST timestep; bsuite_info() stays un-noised / un-scaled.
 template <class F, class R, class WR>
 BSB_HD StepOut lane_transition(const EnvParams& p, int64_t i, typename F::Lane& L, R& rng, WR& wrng,
                                int32_t action, int32_t mode, bool noise) {
@@ -86,10 +103,30 @@ BSB_HD StepOut lane_transition(const EnvParams& p, int64_t i, typename F::Lane& 
   } else {
     o = F::step(p, i, L, action, rng);
     L.nr = (o.step_type == LAST) ? 1u : 0u;
-    if (noise) { if (o.step_type != FIRST) o.reward = o.reward + p.noise_scale * wrng.randn(); }
+    if (noise) { o.reward = o.reward + p.noise_scale * wrng.randn(); }
     else if (p.wrapper == 2) { o.reward = o.reward * p.reward_scale; }
   }
   return o;
+}
+
+// Observation emitter of each family.
+static const int EMIT_ROWS = 0, EMIT_ONEHOT = 1, EMIT_TWOHOT = 2, EMIT_IMAGE = 3;
+template <class F> struct EmitKind { static const int value = EMIT_ROWS; };
+template <> struct EmitKind<DeepSea> { static const int value = EMIT_ONEHOT; };
+template <> struct EmitKind<Catch> { static const int value = EMIT_TWOHOT; };
+template <> struct EmitKind<Mnist> { static const int value = EMIT_IMAGE; };
+static const int ROW_STAGES = 2;      // double-buffered [32, K] stage per warp
+static const int TILE_STAGES = 2;     // deep_sea bulk path: double-buffered groups of `group_lanes` tiles per warp
+
+// Dynamic shared memory per warp, in floats.
+template <class F> inline
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+size_t smem_floats_per_warp(int K, bool emit_bulk, int group_lanes) {
+  if (EmitKind<F>::value == EMIT_ROWS || EmitKind<F>::value == EMIT_TWOHOT) return (size_t)ROW_STAGES * 32 * (size_t)K;
+  if (EmitKind<F>::value == EMIT_ONEHOT && emit_bulk) return (size_t)TILE_STAGES * (size_t)group_lanes * (size_t)K;
+  return 0;
 }
 
 #if defined(__CUDACC__)
@@ -97,17 +134,21 @@ BSB_HD StepOut lane_transition(const EnvParams& p, int64_t i, typename F::Lane& 
 __device__ __forceinline__ void st_stream(float4* dst, float4 v) { __stcs(dst, v); }
 __device__ __forceinline__ void st_stream(float* dst, float v) { __stcs(dst, v); }
 
-// ----- observation emitters -------------------------------------------------
-static const int EMIT_ROWS = 0, EMIT_ONEHOT = 1, EMIT_TWOHOT = 2, EMIT_IMAGE = 3;
-template <class F> struct EmitKind { static const int value = EMIT_ROWS; };
-template <> struct EmitKind<DeepSea> { static const int value = EMIT_ONEHOT; };
-template <> struct EmitKind<Catch> { static const int value = EMIT_TWOHOT; };
-template <> struct EmitKind<Mnist> { static const int value = EMIT_IMAGE; };
+// ----- TMA bulk store (shared::cta -> global) and PDL primitives --------------
+__device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// ----- vector-store emitters ---------------------------------------------------
 // One-hot tiles: `hot` is the flat index of the single 1.0 (or -1: all zeros).
-__device__ __forceinline__ void emit_onehot(float* obs_t, int64_t warp_base, int64_t B, int K, int hot, bool vec) {
+__device__ __forceinline__ void emit_onehot_vec(float* obs_t, int64_t warp_base, int n_lanes, int K, int hot, bool vec) {
   const int tid = threadIdx.x & 31;
-  const int n_lanes = (B - warp_base) < 32 ? (int)(B - warp_base) : 32;
   if (vec) {
     const int K4 = K >> 2;
     for (int j = 0; j < n_lanes; ++j) {
@@ -131,9 +172,8 @@ __device__ __forceinline__ void emit_onehot(float* obs_t, int64_t warp_base, int
 }
 
 // Boards with up to two hot cells; the warp's boards form one contiguous span.
-__device__ __forceinline__ void emit_twohot(float* obs_t, int64_t warp_base, int64_t B, int K, int hot_a, int hot_b, bool vec) {
+__device__ __forceinline__ void emit_twohot_vec(float* obs_t, int64_t warp_base, int n_lanes, int K, int hot_a, int hot_b, bool vec) {
   const int tid = threadIdx.x & 31;
-  const int n_lanes = (B - warp_base) < 32 ? (int)(B - warp_base) : 32;
   const int total = n_lanes * K;
   float* dst = obs_t + warp_base * (int64_t)K;
   if (vec && (total & 3) == 0) {
@@ -166,9 +206,8 @@ __device__ __forceinline__ void emit_twohot(float* obs_t, int64_t warp_base, int
 }
 
 // Image tiles gathered from the int8 dataset (`image` < 0: zeros).
-__device__ __forceinline__ void emit_image(const EnvParams& p, float* obs_t, int64_t warp_base, int64_t B, int K, int image, bool vec) {
+__device__ __forceinline__ void emit_image(const EnvParams& p, float* obs_t, int64_t warp_base, int n_lanes, int K, int image, bool vec) {
   const int tid = threadIdx.x & 31;
-  const int n_lanes = (B - warp_base) < 32 ? (int)(B - warp_base) : 32;
   for (int j = 0; j < n_lanes; ++j) {
     const int img = __shfl_sync(0xffffffffu, image, j);
     float* dst = obs_t + (warp_base + j) * (int64_t)K;
@@ -189,10 +228,9 @@ __device__ __forceinline__ void emit_image(const EnvParams& p, float* obs_t, int
   }
 }
 
-// Stream the warp's staged [n_lanes, K] block.
-__device__ __forceinline__ void flush_rows(const float* stage, float* obs_t, int64_t warp_base, int64_t B, int K, bool vec) {
+// Stream the warp's staged [n_lanes, K] block with ordinary stores (ragged tail warps, unaligned buffers).
+__device__ __forceinline__ void flush_rows_vec(const float* stage, float* obs_t, int64_t warp_base, int n_lanes, int K, bool vec) {
   const int tid = threadIdx.x & 31;
-  const int n_lanes = (B - warp_base) < 32 ? (int)(B - warp_base) : 32;
   const int total = n_lanes * K;
   float* dst = obs_t + warp_base * (int64_t)K;
   if (vec && (total & 3) == 0) {
@@ -203,24 +241,16 @@ __device__ __forceinline__ void flush_rows(const float* stage, float* obs_t, int
   }
 }
 
-template <class F, class R>
-__device__ __forceinline__ void render_row(const EnvParams& p, const typename F::Lane& L, R&, float* dst) { F::row(p, L, dst, 1); }
-template <>
-__device__ __forceinline__ void render_row<UmbrellaChain, LegacyRng<PhiloxSrc> >(const EnvParams& p, const UmbrellaChain::Lane& L, LegacyRng<PhiloxSrc>& r, float* dst) { UmbrellaChain::row(p, L, r, dst, 1); }
-template <>
-__device__ __forceinline__ void render_row<UmbrellaChain, LegacyRng<MtSrc> >(const EnvParams& p, const UmbrellaChain::Lane& L, LegacyRng<MtSrc>& r, float* dst) { UmbrellaChain::row(p, L, r, dst, 1); }
-// Families without a row() never reach render_row (EmitKind != ROWS); give them a stub.
-template <class F> struct HasRow { enum { value = 1 }; };
-template <> struct HasRow<DeepSea> { enum { value = 0 }; };
-template <> struct HasRow<Catch> { enum { value = 0 }; };
-template <> struct HasRow<Mnist> { enum { value = 0 }; };
-
-template <class F, class R, bool kHas> struct RowRenderer {
-  static __device__ __forceinline__ void run(const EnvParams& p, const typename F::Lane& L, R& r, float* dst) { render_row<F, R>(p, L, r, dst); }
+// ----- per-family glue ------------------------------------------------------------
+template <class F, class R> struct RowRenderer {
+  static __device__ __forceinline__ void run(const EnvParams& p, const typename F::Lane& L, R&, float* dst) { F::row(p, L, dst, 1); }
 };
-template <class F, class R> struct RowRenderer<F, R, false> {
-  static __device__ __forceinline__ void run(const EnvParams&, const typename F::Lane&, R&, float*) {}
+template <class R> struct RowRenderer<UmbrellaChain, R> {   // the observation itself draws from the stream
+  static __device__ __forceinline__ void run(const EnvParams& p, const UmbrellaChain::Lane& L, R& r, float* dst) { UmbrellaChain::row(p, L, r, dst, 1); }
 };
+template <class R> struct RowRenderer<DeepSea, R> { static __device__ __forceinline__ void run(const EnvParams&, const DeepSea::Lane&, R&, float*) {} };
+template <class R> struct RowRenderer<Catch, R> { static __device__ __forceinline__ void run(const EnvParams&, const Catch::Lane&, R&, float*) {} };
+template <class R> struct RowRenderer<Mnist, R> { static __device__ __forceinline__ void run(const EnvParams&, const Mnist::Lane&, R&, float*) {} };
 
 template <class F> struct Descriptor {
   static __device__ __forceinline__ int a(const typename F::Lane&) { return -1; }
@@ -239,83 +269,192 @@ template <> struct Descriptor<Mnist> {
   static __device__ __forceinline__ int b(const Mnist::Lane&) { return -1; }
 };
 
-// ----- the fused transition kernel -------------------------------------------
-// Grid: ceil(B / blockDim.x) CTAs of kWarps warps; warp w of the grid owns lanes
-// [32 w, 32 w + 32).  Small CTAs keep the per-SM share of the 2048 warp-tasks of
-// a 65 536-lane batch within ~1% of even on 148 SMs.
-template <class F, int RK, bool kNoise>
+// ----- the fused transition kernel ----------------------------------------------
+// Work unit: a CHUNK of 32 consecutive lanes, processed by one warp (thread = lane).
+//   * default launch: one chunk per warp, ceil(B / 32) warps; small CTAs (64 threads) keep the per-SM share of
+//     the 2048 chunks of a 65 536-lane batch within ~1% of even on 148 SMs and let the hardware CTA scheduler
+//     balance SMs dynamically.
+//   * deep_sea bulk path: a PERSISTENT grid (as many warps as fit the SMs' shared memory) whose warps pull chunk
+//     indices from a global counter (atomicAdd by the elected lane, one fetch kept in flight ahead of use).  SMs
+//     drain HBM at slightly different rates (L2 slice / die distance), so dynamic dealing matters: a static
+//     equal split measured 15% slower.  A warp loads its next chunk's state while the TMA unit is still draining
+//     the previous chunk's stores.  The counter is never reset: launch k starts at work_base_k =
+//     work_base_(k-1) + chunks + warps of launch k-1 (every warp makes exactly one failing fetch).
+template <class F, int RK, bool kNoise, bool kTrack>
 __global__ void __launch_bounds__(128) transition_kernel(const EnvParams p, const LaunchArgs a) {
   typedef typename RngOf<RK>::type R;
+  constexpr int kEmit = EmitKind<F>::value;
   extern __shared__ float4 smem_raw[];
+  const int tid = threadIdx.x & 31, warp = threadIdx.x >> 5, warps_per_cta = blockDim.x >> 5;
   const int64_t B = p.batch;
-  const int64_t lane = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t warp_base = lane - (threadIdx.x & 31);
-  if (warp_base >= B) return;                    // whole warp out of range
-  const bool active = lane < B;
   const int K = p.obs_numel;
-  float* stage = reinterpret_cast<float*>(smem_raw) + (size_t)(threadIdx.x >> 5) * 32 * (size_t)K;
+  const bool vec = a.obs_vec_ok != 0;
+  const size_t stage_floats = smem_floats_per_warp<F>(K, a.emit_bulk != 0, a.group_lanes);
+  float* stage = reinterpret_cast<float*>(smem_raw) + (size_t)warp * stage_floats;
 
-  typename F::Lane L;
-  R rng, wrng;
-  EpisodeStats ep;
-  const bool has_rng = p.rng_pos != nullptr;
-  const bool track = p.ep != nullptr;
-  if (active) {
-    if (a.mode == MODE_INIT) F::init(p, L); else F::load(p, lane, L);
-    if (has_rng) rng_open(rng, p, lane, false);
-    if (kNoise) rng_open(wrng, p, lane, true);
-    if (track) ep.load(p, lane);
-  } else {
-    F::init(p, L);
+  // Stages that rely on staying zero between steps are cleared once, before the dependency wait.
+  if (kEmit == EMIT_TWOHOT || (kEmit == EMIT_ONEHOT && a.emit_bulk)) {
+    float4* s4 = reinterpret_cast<float4*>(stage);
+    const int total4 = (int)(stage_floats >> 2);
+    for (int q = tid; q < total4; q += 32) s4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e = (total4 << 2) + tid; e < (int)stage_floats; e += 32) stage[e] = 0.f;
+    __syncwarp();
   }
+  // Wait for the previous step's kernel (it wrote the lane state read below), THEN allow the next step's kernel
+  // to become resident: its CTAs park at their own wait, so at most one dependent grid is ever pending.
+  if (a.use_pdl) { pdl_wait(); pdl_launch_dependents(); }
 
-  if (a.mode == MODE_INIT) {
+  const int64_t n_chunks = (B + 31) / 32;
+  const bool dynamic = a.work_counter != nullptr;
+  auto fetch_chunk = [&]() -> int64_t {
+    unsigned long long v = 0;
+    if (tid == 0) v = atomicAdd(a.work_counter, 1ull) - a.work_base;
+    return (int64_t)__shfl_sync(0xffffffffu, v, 0);
+  };
+  int64_t next_chunk = dynamic ? fetch_chunk() : (int64_t)blockIdx.x * warps_per_cta + warp;
+
+  const bool has_rng = p.rng_pos != nullptr;
+  // catch: cells this thread poked into stage buffer 0 / 1 (cleared when that buffer is reused)
+  int poked_a0 = -1, poked_b0 = -1, poked_a1 = -1, poked_b1 = -1;
+  // deep_sea bulk path: offset of the cell this thread poked into group buffer 0 / 1 (cleared on reuse)
+  int tile_poked0 = -1, tile_poked1 = -1;
+  unsigned emitted = 0;          // bulk stores issued by this warp so far (double-buffer parity)
+  bool any_bulk = false;
+
+  while (next_chunk < n_chunks) {
+    const int64_t warp_base = next_chunk * 32;
+    next_chunk = dynamic ? fetch_chunk() : n_chunks;      // dynamic: keep one fetch in flight ahead of use
+    const int n_lanes = (B - warp_base) < 32 ? (int)(B - warp_base) : 32;
+    const int64_t lane = warp_base + tid;
+    const bool active = tid < n_lanes;
+    // Bulk (TMA) emission needs 16-byte aligned spans; the choice is warp-uniform per chunk.
+    bool bulk = a.emit_bulk && vec;
+    if (kEmit == EMIT_ROWS) bulk = bulk && K >= 3 && ((n_lanes * K) & 3) == 0;
+    if (kEmit == EMIT_TWOHOT) bulk = bulk && ((n_lanes * K) & 3) == 0;
+    if (kEmit == EMIT_ONEHOT) bulk = bulk && ((K & 3) == 0 || ((n_lanes % a.group_lanes) == 0 && ((a.group_lanes * K) & 3) == 0));
+    if (kEmit == EMIT_IMAGE) bulk = false;
+    any_bulk = any_bulk || bulk;
+
+    typename F::Lane L;
+    R rng, wrng;
+    EpisodeStats ep;
+    ActionStream action_stream;
+    action_stream.open();
     if (active) {
-      F::ctor_draws(p, L, rng);
+      if (a.mode == MODE_INIT) F::init(p, L); else F::load(p, lane, L);
+      if (has_rng) rng_open(rng, p, lane, false);
+      if (kNoise) rng_open(wrng, p, lane, true);
+      if (kTrack) ep.load(p, lane);
+    } else {
+      F::init(p, L);
+    }
+
+    if (a.mode == MODE_INIT) {
+      if (active) {
+        F::ctor_draws(p, L, rng);
+        F::store(p, lane, L);
+        if (has_rng) rng_close(rng, p, lane, false);
+      }
+      continue;
+    }
+
+    for (int64_t t = 0; t < a.T; ++t) {
+      const int64_t off = t * B + lane;
+      if (active) {
+        int32_t action = 0;
+        if (a.mode == MODE_STEP) {
+          action = a.actions ? a.actions[off]
+                             : action_stream.sample(a.action_seed, p.lane_offset + (uint64_t)lane, (uint64_t)(a.step0 + t), p.num_actions);
+          if (a.actions_out) a.actions_out[off] = action;
+        }
+        const StepOut o = lane_transition<F, R, R>(p, lane, L, rng, wrng, action, a.mode, kNoise);
+        if (kTrack) ep.track(o);
+        if (a.reward) a.reward[off] = (float)o.reward;
+        if (a.reward_f64) a.reward_f64[off] = o.reward;
+        if (a.discount) a.discount[off] = o.discount;
+        if (a.step_type) a.step_type[off] = o.step_type;
+      }
+      float* obs_t = a.obs + t * B * (int64_t)K;
+
+      if (kEmit == EMIT_ONEHOT) {
+        const int hot = Descriptor<F>::a(L);
+        if (bulk) {
+          // Groups of m consecutive lanes share one staging buffer (m tiles, contiguous in global memory too) and
+          // leave as ONE bulk store of up to m * 4K bytes: large stores amortise the per-operation cost of the
+          // TMA unit (measured: ~70 ns + bytes / 64 GB/s per SM).
+          const int m = a.group_lanes;
+          for (int g0 = 0; g0 < n_lanes; g0 += m) {
+            const int in_group = (n_lanes - g0) < m ? (n_lanes - g0) : m;
+            const int s = (int)(emitted & 1u);
+            float* group = stage + (size_t)s * m * K;
+            if (tid == 0) bulk_wait_read<TILE_STAGES - 1>();    // the store two back, last reader of `group`, is done
+            __syncwarp();
+            if (s == 0) { if (tile_poked0 >= 0) { group[tile_poked0] = 0.f; tile_poked0 = -1; } }
+            else        { if (tile_poked1 >= 0) { group[tile_poked1] = 0.f; tile_poked1 = -1; } }
+            if (tid >= g0 && tid < g0 + in_group && hot >= 0) {
+              const int cell = (tid - g0) * K + hot;
+              group[cell] = 1.f;
+              if (s == 0) tile_poked0 = cell; else tile_poked1 = cell;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (tid == 0) {
+              bulk_store_s2g(obs_t + (warp_base + g0) * (int64_t)K, group, (uint32_t)in_group * (uint32_t)K * 4u);
+              bulk_commit();
+            }
+            ++emitted;
+          }
+        } else {
+          emit_onehot_vec(obs_t, warp_base, n_lanes, K, hot, vec && (K & 3) == 0);
+        }
+      } else if (kEmit == EMIT_TWOHOT) {
+        const int hot_a = Descriptor<F>::a(L), hot_b = Descriptor<F>::b(L);
+        if (bulk) {
+          const int buf = (int)(emitted & 1u);
+          float* boards = stage + (size_t)buf * 32 * K;
+          if (tid == 0) bulk_wait_read<ROW_STAGES - 1>();      // the store that last read `boards` is done with it
+          __syncwarp();
+          float* mine = boards + tid * K;
+          const int old_a = buf ? poked_a1 : poked_a0, old_b = buf ? poked_b1 : poked_b0;
+          if (old_a >= 0) mine[old_a] = 0.f;
+          if (old_b >= 0) mine[old_b] = 0.f;
+          int new_a = -1, new_b = -1;
+          if (active) { mine[hot_a] = 1.f; mine[hot_b] = 1.f; new_a = hot_a; new_b = hot_b; }
+          if (buf) { poked_a1 = new_a; poked_b1 = new_b; } else { poked_a0 = new_a; poked_b0 = new_b; }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (tid == 0) { bulk_store_s2g(obs_t + warp_base * (int64_t)K, boards, (uint32_t)n_lanes * (uint32_t)K * 4u); bulk_commit(); }
+          ++emitted;
+        } else {
+          emit_twohot_vec(obs_t, warp_base, n_lanes, K, hot_a, hot_b, vec);
+        }
+      } else if (kEmit == EMIT_IMAGE) {
+        emit_image(p, obs_t, warp_base, n_lanes, K, Descriptor<F>::a(L), vec && (K & 3) == 0);
+      } else {
+        float* rows = stage + (size_t)(emitted & 1u) * 32 * K;
+        if (bulk) { if (tid == 0) bulk_wait_read<ROW_STAGES - 1>(); }
+        __syncwarp();
+        if (active) RowRenderer<F, R>::run(p, L, rng, rows + tid * K);
+        if (bulk) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (tid == 0) { bulk_store_s2g(obs_t + warp_base * (int64_t)K, rows, (uint32_t)n_lanes * (uint32_t)K * 4u); bulk_commit(); }
+        } else {
+          __syncwarp();
+          flush_rows_vec(rows, obs_t, warp_base, n_lanes, K, vec);
+        }
+        ++emitted;
+      }
+    }
+
+    if (active) {
       F::store(p, lane, L);
       if (has_rng) rng_close(rng, p, lane, false);
-    }
-    return;
-  }
-
-  for (int64_t t = 0; t < a.T; ++t) {
-    const int64_t off = t * B + lane;
-    if (active) {
-      int32_t action = 0;
-      if (a.mode == MODE_STEP) {
-        action = a.actions ? a.actions[off]
-                           : sample_action(a.action_seed, p.lane_offset + (uint64_t)lane, (uint64_t)(a.step0 + t), p.num_actions);
-        if (a.actions_out) a.actions_out[off] = action;
-      }
-      const StepOut o = lane_transition<F, R, R>(p, lane, L, rng, wrng, action, a.mode, kNoise);
-      if (track) ep.track(o);
-      if (a.reward) a.reward[off] = (float)o.reward;
-      if (a.reward_f64) a.reward_f64[off] = o.reward;
-      if (a.discount) a.discount[off] = o.discount;
-      if (a.step_type) a.step_type[off] = o.step_type;
-    }
-    float* obs_t = a.obs + t * B * (int64_t)K;
-    const bool vec = a.obs_vec_ok && ((K & 3) == 0 || EmitKind<F>::value == EMIT_TWOHOT || EmitKind<F>::value == EMIT_ROWS);
-    if (EmitKind<F>::value == EMIT_ONEHOT) {
-      emit_onehot(obs_t, warp_base, B, K, Descriptor<F>::a(L), vec);
-    } else if (EmitKind<F>::value == EMIT_TWOHOT) {
-      emit_twohot(obs_t, warp_base, B, K, Descriptor<F>::a(L), Descriptor<F>::b(L), vec);
-    } else if (EmitKind<F>::value == EMIT_IMAGE) {
-      emit_image(p, obs_t, warp_base, B, K, Descriptor<F>::a(L), vec);
-    } else {
-      if (active) RowRenderer<F, R, HasRow<F>::value != 0>::run(p, L, rng, stage + (threadIdx.x & 31) * K);
-      __syncwarp();
-      flush_rows(stage, obs_t, warp_base, B, K, vec);
-      __syncwarp();
+      if (kNoise) rng_close(wrng, p, lane, true);
+      if (kTrack) ep.store(p, lane);
     }
   }
-
-  if (active) {
-    F::store(p, lane, L);
-    if (has_rng) rng_close(rng, p, lane, false);
-    if (kNoise) rng_close(wrng, p, lane, true);
-    if (track) ep.store(p, lane);
-  }
+  if (any_bulk && tid == 0) bulk_wait_read<0>();      // shared memory must outlive the last bulk read
 }
 
 #endif  // __CUDACC__

@@ -63,12 +63,27 @@ BSB_HD PhiloxBlock philox4x64_10(u64 c0, u64 c1, u64 c2, u64 c3, u64 k0, u64 k1)
 // Stream ids carried in counter word 3.
 enum : u64 { STREAM_ENV = 0, STREAM_WRAPPER = 1, STREAM_ACTIONS = 2 };
 
-// Uniform action in [0, n) for (action_seed, global lane, global step): one
-// Philox block per (lane, step/4); multiply-shift range reduction.
+// On-device uniform random actions (the workload of baselines/random/agent.py:35-37).
+// The action stream of a lane is the Philox stream (key = (action_seed, global lane), counter word 3 =
+// STREAM_ACTIONS) read as 32-bit chunks: step s uses chunk (s & 7) of block (s >> 3); a chunk r maps to
+// floor(r * n / 2^32) (multiply-shift, no rejection).  One block serves 8 consecutive steps of a lane.
+struct ActionStream {
+  u64 blk_index;          // block currently cached (~0 = none)
+  PhiloxBlock blk;
+  BSB_HD void open() { blk_index = ~0ull; blk.v0 = blk.v1 = blk.v2 = blk.v3 = 0; }
+  BSB_HD int32_t sample(u64 action_seed, u64 global_lane, u64 step, int32_t n) {
+    const u64 want = step >> 3;
+    if (want != blk_index) { blk = philox4x64_10(want, 0, 0, STREAM_ACTIONS, action_seed, global_lane); blk_index = want; }
+    const u32 c = (u32)(step & 7);
+    const u64 w = (c >> 1) == 0 ? blk.v0 : ((c >> 1) == 1 ? blk.v1 : ((c >> 1) == 2 ? blk.v2 : blk.v3));
+    const u32 r = (c & 1) ? (u32)(w >> 32) : (u32)w;
+    return (int32_t)(((u64)r * (u64)(u32)n) >> 32);
+  }
+};
+
 BSB_HD int32_t sample_action(u64 action_seed, u64 global_lane, u64 step, int32_t n) {
-  PhiloxBlock b = philox4x64_10(step, 0, 0, STREAM_ACTIONS, action_seed, global_lane);
-  const u32 r = (u32)(b.v0 >> 32);
-  return (int32_t)(((u64)r * (u64)(u32)n) >> 32);
+  ActionStream s; s.open();
+  return s.sample(action_seed, global_lane, step, n);
 }
 
 // ---------------------------------------------------------------------------

@@ -112,7 +112,8 @@ class StepBuffers:
   def as_outputs(self) -> _lib.Outputs:
     import torch
     out = _lib.Outputs()
-    out.observation = self.observation.data_ptr()
+    if self.observation is not None:
+      out.observation = self.observation.data_ptr()
     if self.reward is not None:
       if self.reward.dtype == torch.float64:
         out.reward_f64 = self.reward.data_ptr()
@@ -222,6 +223,48 @@ class BatchedEnvironment:
     _lib.check(self._lib.bsb_step(self._handle.ptr, ctypes.c_void_p(actions.data_ptr()), ctypes.byref(outputs),
                                   self._stream()))
     return out.timestep()
+
+  def make_host_buffers(self, with_observation: bool = False) -> StepBuffers:
+    """Pinned host tensors for `step_host` (reward / discount / step_type, optionally the observation)."""
+    torch = self._torch
+    pin = self._ordinal >= 0
+    mk = lambda shape, dtype: torch.empty(shape, dtype=dtype, pin_memory=pin)
+    return StepBuffers(
+        observation=mk((self._batch,) + tuple(self._spec.obs_shape), torch.float32) if with_observation else None,
+        reward=mk((self._batch,), self._reward_dtype), discount=mk((self._batch,), torch.float32),
+        step_type=mk((self._batch,), torch.int32))
+
+  def step_host(self, actions, host: StepBuffers, out: Optional[StepBuffers] = None):
+    """One step driven from HOST memory through `bsb_step_host`: actions (CPU int32 tensor, ideally pinned) are
+    copied to the device, the transition kernel runs, and reward / discount / step_type (and the observation if
+    `host.observation` is set) are copied back into `host`; returns after everything has landed.  Observations
+    are also left on the device in `out.observation` for the agent.  Returns (host TimeStep, device observation).
+    """
+    torch = self._torch
+    if not isinstance(actions, torch.Tensor):
+      actions = torch.as_tensor(np.asarray(actions))
+    if actions.device.type != 'cpu' or actions.dtype != torch.int32 or tuple(actions.shape) != (self._batch,):
+      raise ValueError('step_host takes a CPU int32 tensor of shape [batch]')
+    actions = actions.contiguous()
+    out = out or self.make_buffers()
+    houts = _lib.Outputs()
+    if host.observation is not None:
+      houts.observation = host.observation.data_ptr()
+    if host.reward is not None:
+      if host.reward.dtype == torch.float64:
+        houts.reward_f64 = host.reward.data_ptr()
+      else:
+        houts.reward = host.reward.data_ptr()
+    if host.discount is not None:
+      houts.discount = host.discount.data_ptr()
+    if host.step_type is not None:
+      houts.step_type = host.step_type.data_ptr()
+    dev_obs = None if self._ordinal < 0 else ctypes.c_void_p(out.observation.data_ptr())
+    if self._ordinal < 0 and host.observation is None:
+      houts.observation = out.observation.data_ptr()
+    _lib.check(self._lib.bsb_step_host(self._handle.ptr, ctypes.c_void_p(actions.data_ptr()), ctypes.byref(houts), dev_obs))
+    return dm_env.TimeStep(step_type=host.step_type, reward=host.reward, discount=host.discount,
+                           observation=host.observation), out.observation
 
   def rollout(self, num_steps: int, actions=None, action_seed: int = 0, out: Optional[StepBuffers] = None):
     """`num_steps` fused step() calls; actions [T,B] or None for on-device uniform random actions.

@@ -226,7 +226,10 @@ int32_t bsb_read_info(bsb_env* env, int32_t index, double* dst, void* stream);
 /*
  * Logging-wrapper accumulators (utils/wrappers.py:85-110), kept per lane when
  * BSB_FLAG_TRACK_EPISODES is set: field 0 steps, 1 episode, 2 total_return,
- * 3 episode_len, 4 episode_return; float64 [B] each.
+ * 3 episode_len, 4 episode_return; float64 [B] each.  episode_len and
+ * episode_return are zeroed when the NEXT episode starts, so from a LAST
+ * timestep (when the reference writes its row, :99-101) until the lane steps
+ * again they hold the finished episode's values.
  */
 int32_t bsb_read_episode_stats(bsb_env* env, int32_t field, double* dst,
                                void* stream);

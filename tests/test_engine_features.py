@@ -114,35 +114,39 @@ def test_episode_stats_match_reference_logging_wrapper(device):
   for lane in range(B):
     steps = episode = ep_len = 0
     total = ep_ret = 0.0
-    last_len, last_ret = 0, 0.0
     for t in range(T):
       st, r = want['step_type'][t, lane], want['reward'][t, lane]
-      if st != 0:
-        steps += 1; ep_len += 1
+      if st == 0:
+        ep_len, ep_ret = 0, 0.0            # zeroed when the next episode starts
+        continue
+      steps += 1; ep_len += 1
+      ep_ret += r; total += r
       if st == 2:
         episode += 1
-      ep_ret += r if st != 0 else 0.0
-      total += r if st != 0 else 0.0
-      if st == 2:
-        last_len, last_ret, ep_len, ep_ret = ep_len, ep_ret, 0, 0.0
-    got = [stats[k][lane] for k in ('steps', 'episode', 'total_return', 'episode_len', 'episode_return',
-                                    'last_episode_len', 'last_episode_return')]
-    assert got == [steps, episode, total, ep_len, ep_ret, last_len, last_ret]
+    got = [stats[k][lane] for k in ('steps', 'episode', 'total_return', 'episode_len', 'episode_return')]
+    assert got == [steps, episode, total, ep_len, ep_ret]
   if rr.reference_available():
+    # The reference's own Logging wrapper writes its row at LAST timesteps; compare the engine's columns at
+    # exactly such a moment (T2 chosen so that every lane's final call is a LAST: catch episodes are 5 calls).
     rr.import_reference()
     from bsuite.utils import wrappers  # pylint: disable=import-outside-toplevel
+    T2 = 85
+    env2 = bsuite_b200.make('catch', batch=B, device=device, seed=seed, reward_scale=30.0,
+                            engine_kwargs=dict(reward_dtype='float64', track_episodes=True), **kwargs)
+    ts = env2.rollout(T2, actions=torch.as_tensor(actions[:T2]))
+    assert np.all(_np(ts.step_type)[-1] == 2)
+    stats2 = {k: _np(v) for k, v in env2.episode_stats().items()}
     for lane in range(B):
       raw = rr.make_reference_env('catch', kwargs, 'philox', seed, lane, 'scale', 30.0)
       raw.bsuite_num_episodes = 10**9
       recorder = _Recorder()
       logged = wrappers.Logging(raw, recorder, log_every=True)
-      for t in range(T):
+      for t in range(T2):
         logged.step(int(actions[t, lane]))
-      final = recorder.rows[-1]     # written at the most recent LAST timestep
-      assert final['episode'] == stats['episode'][lane]
-      assert final['episode_len'] == stats['last_episode_len'][lane]
-      assert final['episode_return'] == stats['last_episode_return'][lane]
-      assert final['total_regret'] == _np(env.bsuite_info()['total_regret'])[lane]
+      final = recorder.rows[-1]
+      for key in ('steps', 'episode', 'total_return', 'episode_len', 'episode_return'):
+        assert final[key] == stats2[key][lane], key
+      assert final['total_regret'] == _np(env2.bsuite_info()['total_regret'])[lane]
 
 
 @pytest.mark.parametrize('device', DEVICES)
