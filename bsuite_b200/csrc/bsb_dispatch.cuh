@@ -64,7 +64,7 @@ void host_run(const EnvParams& p, const LaunchArgs& a) {
         if (a.actions_out) a.actions_out[off] = action;
       }
       const StepOut o = lane_transition<F, R, R>(p, lane, L, rng, wrng, action, a.mode, noise);
-      if (track) ep.track(o);
+      if (track) ep.track(p, lane, o, a.step0 + t);
       if (a.reward) a.reward[off] = (float)o.reward;
       if (a.reward_f64) a.reward_f64[off] = o.reward;
       if (a.discount) a.discount[off] = o.discount;

@@ -161,10 +161,8 @@ void destroy_env(bsb_env* e) {
   for (size_t k = 0; k < e->allocs.size(); ++k) { if (e->device >= 0) cudaFree(e->allocs[k]); else free(e->allocs[k]); }
   if (e->device >= 0) {
     if (e->h2d_actions) cudaFree(e->h2d_actions);
-    if (e->d_reward) cudaFree(e->d_reward);
+    if (e->d_reward) cudaFree(e->d_reward);      // also owns d_discount / d_step_type
     if (e->d_reward64) cudaFree(e->d_reward64);
-    if (e->d_discount) cudaFree(e->d_discount);
-    if (e->d_step_type) cudaFree(e->d_step_type);
     if (e->d_obs) cudaFree(e->d_obs);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   }
@@ -172,6 +170,11 @@ void destroy_env(bsb_env* e) {
 }
 
 }  // namespace
+
+__global__ void episode_stat_kernel(const EnvParams p, int field, int64_t calls, double* dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < p.batch) dst[i] = episode_stat(p, i, field, calls);
+}
 
 // ============================ extern "C" ====================================
 extern "C" {
@@ -398,7 +401,16 @@ int32_t bsb_read_episode_stats(bsb_env* env, int32_t field, double* dst, void* s
   if (!env || !dst) return fail(BSB_INVALID_ARGUMENT, "null argument");
   if (!env->p.ep) return fail(BSB_INVALID_ARGUMENT, "environment was created without BSB_FLAG_TRACK_EPISODES");
   if (field < 0 || field >= 5) return fail(BSB_INVALID_ARGUMENT, "episode-stat field out of range");
-  return copy_field(env, env->p.ep + (size_t)field * (size_t)env->p.batch, dst, stream);
+  const int64_t B = env->p.batch;
+  if (env->device >= 0) {
+    DeviceGuard guard(env->device);
+    episode_stat_kernel<<<(unsigned)((B + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(env->p, field, env->steps_done, dst);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    BSB_CUDA(cudaGetLastError());
+  } else {
+    for (int64_t i = 0; i < B; ++i) dst[i] = episode_stat(env->p, i, field, env->steps_done);
+  }
+  return BSB_OK;
 }
 
 int32_t bsb_state_bytes(const bsb_env* env, int64_t* nbytes) {
@@ -453,10 +465,14 @@ int32_t bsb_step_host(bsb_env* env, const int32_t* actions, const bsb_outputs* h
   const size_t B = (size_t)env->p.batch, K = (size_t)env->p.obs_numel;
   if (!env->copy_stream) BSB_CUDA(cudaStreamCreateWithFlags(&env->copy_stream, cudaStreamNonBlocking));
   if (!env->h2d_actions) BSB_CUDA(cudaMalloc(&env->h2d_actions, B * 4));
-  if (host_out->reward && !env->d_reward) BSB_CUDA(cudaMalloc(&env->d_reward, B * 4));
+  // reward | discount | step_type live in ONE device block so that a caller who keeps its three host arrays
+  // back to back (BatchedEnvironment.make_host_buffers does) gets them with a single D2H copy.
+  if (!env->d_reward) {
+    BSB_CUDA(cudaMalloc(&env->d_reward, 3 * B * 4));
+    env->d_discount = env->d_reward + B;
+    env->d_step_type = reinterpret_cast<int32_t*>(env->d_reward + 2 * B);
+  }
   if (host_out->reward_f64 && !env->d_reward64) BSB_CUDA(cudaMalloc(&env->d_reward64, B * 8));
-  if (host_out->discount && !env->d_discount) BSB_CUDA(cudaMalloc(&env->d_discount, B * 4));
-  if (host_out->step_type && !env->d_step_type) BSB_CUDA(cudaMalloc(&env->d_step_type, B * 4));
   if (!device_obs && !env->d_obs) BSB_CUDA(cudaMalloc(&env->d_obs, B * K * 4));
   cudaStream_t s = env->copy_stream;
   BSB_CUDA(cudaMemcpyAsync(env->h2d_actions, actions, B * 4, cudaMemcpyHostToDevice, s));
@@ -468,10 +484,17 @@ int32_t bsb_step_host(bsb_env* env, const int32_t* actions, const bsb_outputs* h
   dev.step_type = host_out->step_type ? env->d_step_type : nullptr;
   int rc = bsb_step(env, env->h2d_actions, &dev, s);
   if (rc != BSB_OK) return rc;
-  if (host_out->reward) BSB_CUDA(cudaMemcpyAsync(host_out->reward, dev.reward, B * 4, cudaMemcpyDeviceToHost, s));
+  const bool packed = host_out->reward && host_out->discount && host_out->step_type &&
+                      host_out->discount == host_out->reward + B &&
+                      reinterpret_cast<char*>(host_out->step_type) == reinterpret_cast<char*>(host_out->reward + 2 * B);
+  if (packed) {
+    BSB_CUDA(cudaMemcpyAsync(host_out->reward, env->d_reward, 3 * B * 4, cudaMemcpyDeviceToHost, s));
+  } else {
+    if (host_out->reward) BSB_CUDA(cudaMemcpyAsync(host_out->reward, dev.reward, B * 4, cudaMemcpyDeviceToHost, s));
+    if (host_out->discount) BSB_CUDA(cudaMemcpyAsync(host_out->discount, dev.discount, B * 4, cudaMemcpyDeviceToHost, s));
+    if (host_out->step_type) BSB_CUDA(cudaMemcpyAsync(host_out->step_type, dev.step_type, B * 4, cudaMemcpyDeviceToHost, s));
+  }
   if (host_out->reward_f64) BSB_CUDA(cudaMemcpyAsync(host_out->reward_f64, dev.reward_f64, B * 8, cudaMemcpyDeviceToHost, s));
-  if (host_out->discount) BSB_CUDA(cudaMemcpyAsync(host_out->discount, dev.discount, B * 4, cudaMemcpyDeviceToHost, s));
-  if (host_out->step_type) BSB_CUDA(cudaMemcpyAsync(host_out->step_type, dev.step_type, B * 4, cudaMemcpyDeviceToHost, s));
   if (host_out->observation) BSB_CUDA(cudaMemcpyAsync(host_out->observation, dev.observation, B * K * 4, cudaMemcpyDeviceToHost, s));
   BSB_CUDA(cudaStreamSynchronize(s));
   return BSB_OK;

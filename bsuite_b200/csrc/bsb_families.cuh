@@ -508,29 +508,44 @@ struct Mnist {
   static BSB_HD float pixel(int8_t v) { return (float)v / 255.0f; }
 };
 
-// Logging-wrapper bookkeeping (utils/wrappers.py:85-110) on the wrapped reward, five float64 columns per
-// lane: steps, episode, total_return, episode_len, episode_return.  The reference zeroes episode_len /
-// episode_return right after it has logged a LAST timestep; here they are zeroed when the NEXT episode starts
-// (on FIRST), so at a LAST timestep -- the moment the reference writes its row (:99-101) -- and until the lane
-// steps again they hold the finished episode's values, with no extra "last episode" columns to carry.
+// Logging-wrapper bookkeeping (utils/wrappers.py:85-110) on the wrapped reward.  The reference keeps five columns
+// (steps, episode, total_return, episode_len, episode_return); only the two float sums change on every step, so
+// only they are carried densely (16 B read + 16 B written per lane-step).  The integer columns follow from three
+// values that change at episode boundaries only, because all lanes step in lock-step:
+//   ep[0] total_return     dense      ep[1] episode         += 1 at LAST
+//   ep[2] episode_return   dense      ep[3] first_count     += 1 at FIRST
+//                                     ep[4] start_call      = global call index of the latest FIRST
+//   steps       = calls - first_count              (every call that did not return FIRST is a transition)
+//   episode_len = calls - 1 - start_call           (transitions since the latest FIRST; 0 before any)
+// The reference zeroes episode_len / episode_return right after logging a LAST timestep; here they restart at the
+// NEXT episode's FIRST, so from a LAST timestep -- the moment the reference writes its row (:99-101) -- until the
+// lane steps again they hold the finished episode's values.
 struct EpisodeStats {
-  double steps, episode, total_return, episode_len, episode_return;
-  BSB_HD void load(const EnvParams& p, int64_t i) {
-    const int64_t B = p.batch;
-    steps = p.ep[i]; episode = p.ep[B + i]; total_return = p.ep[2 * B + i]; episode_len = p.ep[3 * B + i];
-    episode_return = p.ep[4 * B + i];
-  }
-  BSB_HD void store(const EnvParams& p, int64_t i) const {
-    const int64_t B = p.batch;
-    p.ep[i] = steps; p.ep[B + i] = episode; p.ep[2 * B + i] = total_return; p.ep[3 * B + i] = episode_len;
-    p.ep[4 * B + i] = episode_return;
-  }
-  BSB_HD void track(const StepOut& o) {
-    if (o.step_type == FIRST) { episode_len = 0.0; episode_return = 0.0; return; }
-    steps += 1.0; episode_len += 1.0;
+  double total_return, episode_return;
+  BSB_HD void load(const EnvParams& p, int64_t i) { total_return = p.ep[i]; episode_return = p.ep[2 * p.batch + i]; }
+  BSB_HD void store(const EnvParams& p, int64_t i) const { p.ep[i] = total_return; p.ep[2 * p.batch + i] = episode_return; }
+  BSB_HD void track(const EnvParams& p, int64_t i, const StepOut& o, int64_t call_index) {
+    if (o.step_type == FIRST) {
+      episode_return = 0.0;
+      p.ep[3 * p.batch + i] += 1.0;
+      p.ep[4 * p.batch + i] = (double)call_index;
+      return;
+    }
     episode_return += o.reward; total_return += o.reward;
-    if (o.step_type == LAST) episode += 1.0;
+    if (o.step_type == LAST) p.ep[p.batch + i] += 1.0;
   }
 };
+
+// Column `field` (0 steps, 1 episode, 2 total_return, 3 episode_len, 4 episode_return) of lane i after `calls` calls.
+BSB_HD double episode_stat(const EnvParams& p, int64_t i, int field, int64_t calls) {
+  const int64_t B = p.batch;
+  switch (field) {
+    case 0: return (double)calls - p.ep[3 * B + i];
+    case 1: return p.ep[B + i];
+    case 2: return p.ep[i];
+    case 3: return p.ep[3 * B + i] == 0.0 ? 0.0 : (double)(calls - 1) - p.ep[4 * B + i];
+    default: return p.ep[2 * B + i];
+  }
+}
 
 }  // namespace bsb

@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(128) transition_kernel(const EnvParams p, cons
           if (a.actions_out) a.actions_out[off] = action;
         }
         const StepOut o = lane_transition<F, R, R>(p, lane, L, rng, wrng, action, a.mode, kNoise);
-        if (kTrack) ep.track(o);
+        if (kTrack) ep.track(p, lane, o, a.step0 + t);
         if (a.reward) a.reward[off] = (float)o.reward;
         if (a.reward_f64) a.reward_f64[off] = o.reward;
         if (a.discount) a.discount[off] = o.discount;

@@ -225,14 +225,23 @@ class BatchedEnvironment:
     return out.timestep()
 
   def make_host_buffers(self, with_observation: bool = False) -> StepBuffers:
-    """Pinned host tensors for `step_host` (reward / discount / step_type, optionally the observation)."""
+    """Pinned host tensors for `step_host` (reward / discount / step_type, optionally the observation).
+
+    The three scalar arrays are views of ONE pinned block, back to back, so `bsb_step_host` returns them with a
+    single device-to-host copy."""
     torch = self._torch
     pin = self._ordinal >= 0
-    mk = lambda shape, dtype: torch.empty(shape, dtype=dtype, pin_memory=pin)
-    return StepBuffers(
-        observation=mk((self._batch,) + tuple(self._spec.obs_shape), torch.float32) if with_observation else None,
-        reward=mk((self._batch,), self._reward_dtype), discount=mk((self._batch,), torch.float32),
-        step_type=mk((self._batch,), torch.int32))
+    B = self._batch
+    if self._reward_dtype == torch.float32:
+      block = torch.empty(3 * B, dtype=torch.float32, pin_memory=pin)
+      reward, discount, step_type = block[:B], block[B:2 * B], block[2 * B:].view(torch.int32)
+    else:
+      reward = torch.empty(B, dtype=torch.float64, pin_memory=pin)
+      discount = torch.empty(B, dtype=torch.float32, pin_memory=pin)
+      step_type = torch.empty(B, dtype=torch.int32, pin_memory=pin)
+    observation = (torch.empty((B,) + tuple(self._spec.obs_shape), dtype=torch.float32, pin_memory=pin)
+                   if with_observation else None)
+    return StepBuffers(observation=observation, reward=reward, discount=discount, step_type=step_type)
 
   def step_host(self, actions, host: StepBuffers, out: Optional[StepBuffers] = None):
     """One step driven from HOST memory through `bsb_step_host`: actions (CPU int32 tensor, ideally pinned) are
@@ -260,9 +269,11 @@ class BatchedEnvironment:
     if host.step_type is not None:
       houts.step_type = host.step_type.data_ptr()
     dev_obs = None if self._ordinal < 0 else ctypes.c_void_p(out.observation.data_ptr())
-    if self._ordinal < 0 and host.observation is None:
+    if self._ordinal < 0:        # host environment: one memory space; `out.observation` is the observation
       houts.observation = out.observation.data_ptr()
     _lib.check(self._lib.bsb_step_host(self._handle.ptr, ctypes.c_void_p(actions.data_ptr()), ctypes.byref(houts), dev_obs))
+    if self._ordinal < 0 and host.observation is not None:
+      host.observation.copy_(out.observation)
     return dm_env.TimeStep(step_type=host.step_type, reward=host.reward, discount=host.discount,
                            observation=host.observation), out.observation
 

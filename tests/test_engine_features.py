@@ -159,3 +159,24 @@ def test_unsupported_configurations_are_rejected(device):
   env = bsuite_b200.load_from_id('catch/0', batch=4, device=device)
   with pytest.raises(ValueError, match='shape'):
     env.step(torch.zeros(5, dtype=torch.int32))
+
+
+@pytest.mark.parametrize('device', DEVICES)
+@pytest.mark.parametrize('with_obs', [False, True])
+def test_step_host_matches_step(device, with_obs):
+  """`bsb_step_host` (host actions in, host scalars out, observation left on the device) == `bsb_step`."""
+  a = bsuite_b200.load_from_id('deep_sea_stochastic/3', batch=96, device=device, seed=2)
+  b = bsuite_b200.load_from_id('deep_sea_stochastic/3', batch=96, device=device, seed=2)
+  host = b.make_host_buffers(with_observation=with_obs)
+  actions = torch.as_tensor(np.random.RandomState(3).randint(2, size=(40, 96)).astype(np.int32))
+  if device != 'cpu':
+    actions = actions.pin_memory()
+  for t in range(40):
+    want = a.step(actions[t])
+    got, dev_obs = b.step_host(actions[t], host)
+    np.testing.assert_array_equal(_np(got.step_type), _np(want.step_type))
+    np.testing.assert_array_equal(_np(got.reward), _np(want.reward))
+    np.testing.assert_array_equal(_np(got.discount), _np(want.discount))
+    np.testing.assert_array_equal(_np(dev_obs), _np(want.observation))
+    if with_obs:
+      np.testing.assert_array_equal(_np(got.observation), _np(want.observation))
