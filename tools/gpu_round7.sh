@@ -1,0 +1,14 @@
+#!/bin/bash
+set -x
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log; tail -4 gpurun_out/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
+timeout 600 python bench.py --steps 2000 --warmup 20 > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "rc=$?" >> gpurun_out/bench.err; tail -n 1 gpurun_out/bench.log; tail -3 gpurun_out/bench.err
+timeout 600 python bench.py --steps 2000 --warmup 20 --skip-cpu-baseline --no-track > gpurun_out/bench_notrack.log 2>> gpurun_out/bench.err; tail -n 1 gpurun_out/bench_notrack.log | cut -c1-250
+timeout 600 python bench.py --impl reference --steps 400 --warmup 3 > gpurun_out/bench_reference.log 2>> gpurun_out/bench.err; tail -n 1 gpurun_out/bench_reference.log | cut -c1-400
+timeout 900 python tools/bench_families.py --out gpurun_out/families.jsonl > gpurun_out/families.log 2>&1; cat gpurun_out/families.log
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches.csv \
+  python bench.py --steps 40 --warmup 3 --skip-cpu-baseline --skip-host-obs > gpurun_out/ncu_launches.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:transition_kernel -s 30 -c 2 -o gpurun_out/prof_deep_sea_r1 \
+  python bench.py --steps 40 --warmup 3 --skip-cpu-baseline --skip-host-obs > gpurun_out/ncu_full.log 2>&1
+ls -la gpurun_out | head -40
