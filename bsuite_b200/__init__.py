@@ -26,6 +26,9 @@ from bsuite_b200 import sweep  # noqa: E402,F401
 from bsuite_b200.registry import (  # noqa: E402,F401
     EXPERIMENT_NAME_TO_ENVIRONMENT,
     load,
+    load_and_record,
+    load_and_record_to_csv,
+    load_and_record_to_terminal,
     load_from_id,
     make,
     unpack_bsuite_id,

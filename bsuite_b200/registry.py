@@ -62,6 +62,27 @@ def make(environment_class: str, batch: Optional[int] = None, device='cuda', see
   return _instantiate(spec, batch, device, seed, rng, **(engine_kwargs or {}))
 
 
+def load_and_record_to_csv(bsuite_id: str, results_dir: str, overwrite: bool = False, **kwargs):
+  """A bsuite environment that saves results to CSV, loadable by the reference's csv_load (bsuite.py:126-157)."""
+  from bsuite_b200 import recording  # pylint: disable=import-outside-toplevel
+  return recording.Recorder(load_from_id(bsuite_id, **kwargs), recording.CsvLogger(bsuite_id, results_dir, overwrite))
+
+
+def load_and_record_to_terminal(bsuite_id: str, **kwargs):
+  """A bsuite environment that logs to the terminal (bsuite.py:160-167)."""
+  from bsuite_b200 import recording  # pylint: disable=import-outside-toplevel
+  return recording.Recorder(load_from_id(bsuite_id, **kwargs), recording.TerminalLogger())
+
+
+def load_and_record(bsuite_id: str, save_path: str, logging_mode: str = 'csv', overwrite: bool = False, **kwargs):
+  """CSV or terminal logging by `logging_mode` (bsuite.py:111-123)."""
+  if logging_mode == 'csv':
+    return load_and_record_to_csv(bsuite_id, save_path, overwrite, **kwargs)
+  if logging_mode == 'terminal':
+    return load_and_record_to_terminal(bsuite_id, **kwargs)
+  raise ValueError(f'Unrecognised logging_mode "{logging_mode}". Must be "csv" or "terminal".')
+
+
 # experiment name -> loader accepting that experiment's kwargs (bsuite.py:57-81)
 EXPERIMENT_NAME_TO_ENVIRONMENT = {
     name: functools.partial(lambda _name, **kw: load(_name, kw), name)

@@ -1,0 +1,112 @@
+"""Recorder / CsvLogger: the Logging bookkeeping pinned by the reference's utils/wrappers_test.py:84-121, the log
+schedule of wrappers.py:140-147, and CSV files the reference's own csv_load can read."""
+
+import os
+
+import numpy as np
+import pytest
+
+import bsuite_b200
+from bsuite_b200 import dm_env
+from bsuite_b200 import recording
+from oracle import reference_runner as rr
+
+
+class _Cycle(dm_env.Environment):
+  """Replays canned timesteps (the FakeEnvironment of utils/wrappers_test.py:32-79)."""
+  bsuite_num_episodes = 1000
+
+  def __init__(self, timesteps):
+    self._timesteps, self._i = timesteps, 0
+
+  def _next(self):
+    ts = self._timesteps[self._i % len(self._timesteps)]
+    self._i += 1
+    return ts
+
+  def reset(self):
+    self._i = 0
+    return self._next()
+
+  def step(self, action):
+    return self._next()
+
+  def observation_spec(self):
+    return dm_env.specs.Array((), np.float32)
+
+  def action_spec(self):
+    return dm_env.specs.DiscreteArray(1)
+
+  def bsuite_info(self):
+    return {}
+
+
+class _Rows:
+  def __init__(self):
+    self.rows = []
+
+  def write(self, data):
+    self.rows.append(dict(data))
+
+
+def test_bookkeeping_matches_reference_wrapper_test():
+  """The one numeric pin in the reference repo: 5 episodes of rewards (1, 2, 3) with log_every=True."""
+  timesteps = [dm_env.restart([]), dm_env.transition(1, []), dm_env.transition(2, []), dm_env.termination(3, [])]
+  rows = _Rows()
+  env = recording.Recorder(_Cycle(timesteps), rows, log_every=True)
+  for _ in range(5):
+    ts = env.reset()
+    while not ts.last():
+      ts = env.step(0)
+  assert rows.rows == [dict(steps=3 * i, episode=i, total_return=6 * i, episode_len=3, episode_return=6)
+                       for i in range(1, 6)]
+
+
+def test_log_schedule():
+  points = [n for n in range(1, 10001) if recording.is_log_point(n)]
+  assert points[:14] == [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 14, 17, 20]
+  assert len(points) == 49 and points[-1] == 10000          # 49 writes in 10 000 episodes
+
+
+def test_csv_recorder_round_trip(tmp_path):
+  env = bsuite_b200.load_and_record_to_csv('catch/3', str(tmp_path), device='cpu', seed=1)
+  assert env.bsuite_num_episodes == 10000 and env.raw_env is not env
+  rng = np.random.RandomState(0)
+  for _ in range(25):
+    ts = env.reset()
+    while not ts.last():
+      ts = env.step(int(rng.randint(3)))
+  path = tmp_path / 'bsuite_id_-_catch-3.csv'
+  lines = path.read_text().strip().splitlines()
+  assert lines[0] == 'steps,episode,total_return,episode_len,episode_return,total_regret'
+  episodes = [int(line.split(',')[1]) for line in lines[1:]]
+  assert episodes == [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 14, 17, 20, 25]
+  assert all(line.split(',')[3] == '9' for line in lines[1:])        # catch episodes are 9 transitions
+  with pytest.raises(ValueError, match='already exists'):
+    bsuite_b200.load_and_record_to_csv('catch/3', str(tmp_path), device='cpu')
+  with pytest.raises(ValueError, match='logging_mode'):
+    bsuite_b200.load_and_record('catch/3', str(tmp_path), logging_mode='sqlite', device='cpu')
+
+
+@pytest.mark.skipif(not rr.reference_available(), reason='/root/reference only exists in the build container')
+def test_reference_csv_load_reads_our_files(tmp_path):
+  """Same seed, same actions -> the reference's Logging + csv_logging and ours write identical tables, and the
+  reference's csv_load.load_bsuite parses ours."""
+  bsuite = rr.import_reference()
+  from bsuite.logging import csv_load, csv_logging  # pylint: disable=import-outside-toplevel
+  from bsuite.environments import catch as ref_catch  # pylint: disable=import-outside-toplevel
+  ours_dir, ref_dir = str(tmp_path / 'ours'), str(tmp_path / 'ref')
+  ours = recording.Recorder(bsuite_b200.make('catch', device='cpu', seed=5),
+                            recording.CsvLogger('catch/0', ours_dir))
+  ref = csv_logging.wrap_environment(ref_catch.Catch(seed=5), 'catch/0', ref_dir)
+  rng = np.random.RandomState(1)
+  for _ in range(30):
+    a, b = ours.reset(), ref.reset()
+    while not a.last():
+      action = int(rng.randint(3))
+      a, b = ours.step(action), ref.step(action)
+      assert a.reward == b.reward
+  df_ours, _ = csv_load.load_bsuite(ours_dir)
+  df_ref, _ = csv_load.load_bsuite(ref_dir)
+  columns = ['steps', 'episode', 'total_return', 'episode_len', 'episode_return', 'total_regret', 'bsuite_id']
+  assert df_ours[columns].reset_index(drop=True).equals(df_ref[columns].reset_index(drop=True))
