@@ -308,6 +308,31 @@ def engine_main(args):
   if not args.skip_host_obs:
     host_obs_value = timed_e2e(5, env.make_host_buffers(with_observation=True))
 
+  # ---- the T-fused variant (SURVEY.md 8d asks for both): 16 steps per launch, on-device Philox actions -------
+  fused = None
+  if not args.skip_fused:
+    Tf, reps = 16, 8
+    fbuf = [env.make_buffers(Tf) for _ in range(2)]          # 2 x 4.3 GB of observations
+    for i in range(2):
+      env.rollout(Tf, out=fbuf[i % 2])
+    torch.cuda.synchronize()
+    if world > 1:
+      dist.barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(reps):
+      env.rollout(Tf, out=fbuf[i % 2])
+    f1.record()
+    torch.cuda.synchronize()
+    fms = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device=device)
+    if world > 1:
+      dist.all_reduce(fms, op=dist.ReduceOp.MAX)
+    per_step_s = float(fms[0]) * 1e-3 / (reps * Tf)
+    fused = {'T': Tf, 'value': world * B / per_step_s, 'unit': 'env-steps/s', 'us_per_step': per_step_s * 1e6,
+             'achieved_gbs': ALGO_BYTES_PER_LANE_STEP * B / per_step_s / 1e9,
+             'note': 'bsb_rollout: 16 steps per launch, lane state in registers, actions sampled on device'}
+    del fbuf
+
   if rank == 0:
     peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(peaks_path):
@@ -326,18 +351,19 @@ def engine_main(args):
                                   'per-rank episode returns at the log point inside the timed region',
                    'l2_policy': f'outputs cycle through {RING} buffer sets ({RING * B * SIZE * SIZE * 4 / 1e9:.2f} GB '
                                 'of observations > 126 MB L2)',
-                   'launch': 'one transition_kernel launch per step (T = 1)',
+                   'launch': 'value / roofline: one transition_kernel launch per step (T = 1, programmatic dependent launch); the T-fused variant is reported under fused_rollout',
                    'track_episodes': not args.no_track},
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                      'traffic': None, 'peak_source': peak_src,
                      'algorithmic_bytes_per_launch': ALGO_BYTES_PER_LANE_STEP * B,
-                     'launch_us': launch_s * 1e6, 'kernel': 'transition_kernel<DeepSea, Philox, no-noise>'},
+                     'launch_us': launch_s * 1e6, 'kernel': 'transition_kernel<DeepSea, Philox, no-noise, track>: persistent grid, TMA bulk stores of 8 tiles (32 KB)'},
         'cpu_baseline': cpu_baseline,
         'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 4 * B, 'd2h_bytes_per_step': 12 * B,
                 'steps': Ke, 'host_obs_value': host_obs_value,
                 'host_obs_d2h_bytes_per_step': 4 * B * SIZE * SIZE + 12 * B,
                 'note': 'value: observations stay on the device (the API contract); host_obs_value also copies them out'},
         'gpu_launches': int(launches),
+        'fused_rollout': fused,
         'clocks': clocks,
         'log_point': None if summary is None else [float(x) for x in summary.cpu()[:3]],
     }
@@ -356,6 +382,7 @@ def main():
   parser.add_argument('--skip-cpu-baseline', action='store_true')
   parser.add_argument('--skip-host-obs', action='store_true')
   parser.add_argument('--no-track', action='store_true', help='disable the per-lane Logging accumulators')
+  parser.add_argument('--skip-fused', action='store_true', help='skip the T-fused rollout variant')
   args = parser.parse_args()
   if args.warmup < 3:
     args.warmup = 3

@@ -88,6 +88,8 @@ int device_launch(bsb_env* e, LaunchArgs a, cudaStream_t stream) {
   a.group_lanes = 1;
   a.work_counter = nullptr;
   a.work_base = 0;
+  a.fetch_ahead = e->fetch_ahead;
+  a.chunk_lanes = 32;
   int threads = e->block_threads;
   bool persistent = false;
   if (is_onehot && a.emit_bulk) {
@@ -120,6 +122,7 @@ int device_launch(bsb_env* e, LaunchArgs a, cudaStream_t stream) {
       grid = resident;
       a.work_counter = e->work_counter;
       a.work_base = e->work_base;
+      if (e->deep_sea_chunk == 16 && a.group_lanes <= 16) a.chunk_lanes = 16;
     } else {
       persistent = false;      // everything is resident anyway: one chunk per warp
     }
@@ -138,7 +141,7 @@ int device_launch(bsb_env* e, LaunchArgs a, cudaStream_t stream) {
     cfg.numAttrs = 1;
   }
   BSB_CUDA(cudaLaunchKernelEx(&cfg, kernel, e->p, a));
-  if (a.work_counter) e->work_base += (unsigned long long)((B + 31) / 32) + (unsigned long long)grid * (unsigned long long)(threads / 32);
+  if (a.work_counter) e->work_base += (unsigned long long)((B + a.chunk_lanes - 1) / a.chunk_lanes) + (a.fetch_ahead == 1 ? 2ull : 1ull) * (unsigned long long)grid * (unsigned long long)(threads / 32);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return BSB_OK;
 }

@@ -49,6 +49,8 @@ struct LaunchArgs {
   int32_t emit_bulk;        // use TMA bulk stores where the emitter supports them
   int32_t use_pdl;          // launched with programmatic stream serialization
   int32_t group_lanes;      // deep_sea bulk path: lanes per bulk store (power of two, 1..32)
+  int32_t fetch_ahead;      // persistent launches: chunk reservation policy (0 one ahead, 1 two ahead, 2 lazy)
+  int32_t chunk_lanes;      // lanes per chunk (32; the deep_sea persistent path may use 16 for a finer tail)
   int32_t reserved;
   unsigned long long* work_counter;  // persistent launches: monotonically increasing chunk counter (device)
   unsigned long long work_base;      // value of *work_counter at which this launch's chunk 0 starts
@@ -279,7 +281,8 @@ template <> struct Descriptor<Mnist> {
 //     drain HBM at slightly different rates (L2 slice / die distance), so dynamic dealing matters: a static
 //     equal split measured 15% slower.  A warp loads its next chunk's state while the TMA unit is still draining
 //     the previous chunk's stores.  The counter is never reset: launch k starts at work_base_k =
-//     work_base_(k-1) + chunks + warps of launch k-1 (every warp makes exactly one failing fetch).
+//     work_base_(k-1) + chunks + 2 * warps of launch k-1 (every warp makes exactly two failing fetches: the one
+//     that ends its loop and the one already in flight behind it).
 template <class F, int RK, bool kNoise, bool kTrack>
 __global__ void __launch_bounds__(128) transition_kernel(const EnvParams p, const LaunchArgs a) {
   typedef typename RngOf<RK>::type R;
@@ -304,14 +307,22 @@ __global__ void __launch_bounds__(128) transition_kernel(const EnvParams p, cons
   // to become resident: its CTAs park at their own wait, so at most one dependent grid is ever pending.
   if (a.use_pdl) { pdl_wait(); pdl_launch_dependents(); }
 
-  const int64_t n_chunks = (B + 31) / 32;
+  const int CH = a.chunk_lanes;
+  const int64_t n_chunks = (B + CH - 1) / CH;
   const bool dynamic = a.work_counter != nullptr;
-  auto fetch_chunk = [&]() -> int64_t {
-    unsigned long long v = 0;
-    if (tid == 0) v = atomicAdd(a.work_counter, 1ull) - a.work_base;
-    return (int64_t)__shfl_sync(0xffffffffu, v, 0);
-  };
-  int64_t next_chunk = dynamic ? fetch_chunk() : (int64_t)blockIdx.x * warps_per_cta + warp;
+  // Dynamic dealing keeps TWO fetches ahead of use: the elected lane issues an atomicAdd and only broadcasts its
+  // result one chunk later, so neither the atomic round trip nor (below) the next chunk's action loads -- which
+  // may come from pinned HOST memory over PCIe in the zero-copy bsb_step_host path -- sit on the critical path.
+  unsigned long long pending = 0;                // elected lane: result of the fetch in flight
+  auto issue_fetch = [&]() { if (tid == 0) pending = atomicAdd(a.work_counter, 1ull) - a.work_base; };
+  auto collect_fetch = [&]() -> int64_t { return (int64_t)__shfl_sync(0xffffffffu, pending, 0); };
+  int64_t cur_chunk;
+  const bool ahead = a.fetch_ahead == 1, lazy = a.fetch_ahead == 2;
+  if (dynamic) { issue_fetch(); cur_chunk = collect_fetch(); if (ahead) issue_fetch(); }
+  else cur_chunk = (int64_t)blockIdx.x * warps_per_cta + warp;
+  const bool prefetch_actions = ahead && a.actions != nullptr && a.T == 1 && a.mode == MODE_STEP;
+  int32_t ahead_action = 0;                      // action of lane (cur_chunk * 32 + tid), loaded one chunk early
+  if (prefetch_actions && cur_chunk < n_chunks && tid < CH && cur_chunk * CH + tid < B) ahead_action = a.actions[cur_chunk * CH + tid];
 
   const bool has_rng = p.rng_pos != nullptr;
   // catch: cells this thread poked into stage buffer 0 / 1 (cleared when that buffer is reused)
@@ -321,10 +332,14 @@ __global__ void __launch_bounds__(128) transition_kernel(const EnvParams p, cons
   unsigned emitted = 0;          // bulk stores issued by this warp so far (double-buffer parity)
   bool any_bulk = false;
 
-  while (next_chunk < n_chunks) {
-    const int64_t warp_base = next_chunk * 32;
-    next_chunk = dynamic ? fetch_chunk() : n_chunks;      // dynamic: keep one fetch in flight ahead of use
-    const int n_lanes = (B - warp_base) < 32 ? (int)(B - warp_base) : 32;
+  while (cur_chunk < n_chunks) {
+    const int64_t warp_base = cur_chunk * CH;
+    const int32_t my_action = ahead_action;
+    if (dynamic && !ahead && !lazy) issue_fetch();         // default: reserve the next chunk now (one chunk ahead)
+    cur_chunk = (dynamic && !lazy) ? collect_fetch() : n_chunks;   // ahead: this fetch was issued a chunk ago
+    if (dynamic && ahead) issue_fetch();
+    if (prefetch_actions && cur_chunk < n_chunks && tid < CH && cur_chunk * CH + tid < B) ahead_action = a.actions[cur_chunk * CH + tid];
+    const int n_lanes = (B - warp_base) < CH ? (int)(B - warp_base) : CH;
     const int64_t lane = warp_base + tid;
     const bool active = tid < n_lanes;
     // Bulk (TMA) emission needs 16-byte aligned spans; the choice is warp-uniform per chunk.
@@ -355,6 +370,7 @@ __global__ void __launch_bounds__(128) transition_kernel(const EnvParams p, cons
         F::store(p, lane, L);
         if (has_rng) rng_close(rng, p, lane, false);
       }
+      if (dynamic && lazy) { issue_fetch(); cur_chunk = collect_fetch(); }
       continue;
     }
 
@@ -363,8 +379,9 @@ __global__ void __launch_bounds__(128) transition_kernel(const EnvParams p, cons
       if (active) {
         int32_t action = 0;
         if (a.mode == MODE_STEP) {
-          action = a.actions ? a.actions[off]
-                             : action_stream.sample(a.action_seed, p.lane_offset + (uint64_t)lane, (uint64_t)(a.step0 + t), p.num_actions);
+          action = prefetch_actions ? my_action
+                 : (a.actions ? a.actions[off]
+                              : action_stream.sample(a.action_seed, p.lane_offset + (uint64_t)lane, (uint64_t)(a.step0 + t), p.num_actions));
           if (a.actions_out) a.actions_out[off] = action;
         }
         const StepOut o = lane_transition<F, R, R>(p, lane, L, rng, wrng, action, a.mode, kNoise);
@@ -453,6 +470,7 @@ __global__ void __launch_bounds__(128) transition_kernel(const EnvParams p, cons
       if (kNoise) rng_close(wrng, p, lane, true);
       if (kTrack) ep.store(p, lane);
     }
+    if (dynamic && lazy) { issue_fetch(); cur_chunk = collect_fetch(); }   // lazy: nothing reserved while working
   }
   if (any_bulk && tid == 0) bulk_wait_read<0>();      // shared memory must outlive the last bulk read
 }

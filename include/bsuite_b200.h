@@ -246,6 +246,9 @@ int32_t bsb_set_state(bsb_env* env, const void* src_host, int64_t nbytes,
  * outputs back into HOST buffers (`host_out`; NULL members are skipped, so an
  * agent that consumes observations on the device passes observation = NULL and
  * supplies `device_obs`, a device pointer that receives them).  Synchronous.
+ * When `actions` and the requested scalar outputs are PINNED host memory the
+ * kernel accesses them in place over PCIe (zero-copy: no separate H2D / D2H
+ * copies); pageable buffers take the staged-copy path.
  */
 int32_t bsb_step_host(bsb_env* env, const int32_t* actions,
                       const bsb_outputs* host_out, float* device_obs);

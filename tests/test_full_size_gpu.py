@@ -120,3 +120,25 @@ def test_float_dynamics_full_batch(bsuite_id, env_class, kwargs):
     np.testing.assert_array_equal(st[:, lane].cpu().numpy(), want['step_type'][:, 0])
     np.testing.assert_allclose(reward[:, lane].cpu().numpy(), want['reward'][:, 0], rtol=0, atol=1e-6)
     np.testing.assert_allclose(obs[:, lane].cpu().numpy(), want['observation'][:, 0], rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize('bsuite_id,batch', [('deep_sea/0', 100000), ('deep_sea/3', 70001), ('deep_sea/20', 20011),
+                                             ('deep_sea_stochastic/11', 40000)])
+def test_deep_sea_bulk_path_equals_vector_path_at_scale(bsuite_id, batch, monkeypatch):
+  """Large (and ragged) batches take the persistent TMA bulk-store path; it must agree bit for bit with the plain
+  16-byte-store path on every lane, for fused rollouts and for single-step launches (PDL + chunk counter)."""
+  results = []
+  for bulk in ('0', '1'):
+    monkeypatch.setenv('BSB_DEEP_SEA_BULK', bulk)
+    env = bsuite_b200.load_from_id(bsuite_id, batch=batch, device='cuda', seed=11, reward_dtype='float64')
+    ts = env.rollout(12, action_seed=4)
+    got = [ts.step_type.clone(), ts.reward.clone(), ts.observation.clone()]
+    more = torch.as_tensor(env.random_actions(5, action_seed=4))
+    for k in range(5):
+      one = env.step(more[k])
+      got += [one.observation.clone(), one.reward.clone()]
+    got += [v.clone() for v in env.bsuite_info().values()]
+    results.append(got)
+    env.close()
+  for a, b in zip(*results):
+    assert torch.equal(a, b)
