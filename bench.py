@@ -182,6 +182,23 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- engine arm
+def measured_traffic_bytes():
+  """dram__bytes_read.sum + dram__bytes_write.sum per launch of the headline kernel, from the committed `ncu --set
+  full` capture under profiles/ (tools/extract_ncu.py); None when no capture is committed."""
+  import csv
+  import glob
+  paths = sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r*_deep_sea_bulk_ncu_metrics.csv')))
+  if not paths:
+    return None, None
+  scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+  total = 0.0
+  with open(paths[-1]) as fh:
+    for row in csv.reader(fh):
+      if row and row[0] in ('dram__bytes_read.sum', 'dram__bytes_write.sum') and len(row) > 2:
+        total += float(row[2].replace(',', '')) * scale.get(row[1], 1.0)
+  return (total or None), os.path.relpath(paths[-1], ROOT)
+
+
 def engine_main(args):
   import torch
   import torch.distributed as dist
@@ -341,6 +358,7 @@ def engine_main(args):
       peak, peak_src = FALLBACK_HBM_GBS, 'fallback 6.65 TB/s (B200_PROFILING.md)'
     launch_s = (step_ms * 1e-3) / K
     achieved = ALGO_BYTES_PER_LANE_STEP * B / launch_s / 1e9
+    traffic, traffic_src = measured_traffic_bytes()
     line = {
         'metric': METRIC, 'value': value, 'unit': 'env-steps/s', 'n_gpus': world, 'steps': K, 'warmup': W,
         'ms_per_step': total_ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -354,7 +372,7 @@ def engine_main(args):
                    'launch': 'value / roofline: one transition_kernel launch per step (T = 1, programmatic dependent launch); the T-fused variant is reported under fused_rollout',
                    'track_episodes': not args.no_track},
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                     'traffic': None, 'peak_source': peak_src,
+                     'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src,
                      'algorithmic_bytes_per_launch': ALGO_BYTES_PER_LANE_STEP * B,
                      'launch_us': launch_s * 1e6, 'kernel': 'transition_kernel<DeepSea, Philox, no-noise, track>: persistent grid, TMA bulk stores of 8 tiles (32 KB)'},
         'cpu_baseline': cpu_baseline,

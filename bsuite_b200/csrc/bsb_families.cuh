@@ -197,9 +197,24 @@ struct PoleState { double x, x_dot, theta, theta_dot, t; };
 // cartpole.py:37-65 (step_cartpole): explicit Euler from the OLD state; the
 // operation order below is the reference's expression order, and this file is
 // compiled with FMA contraction off.
-BSB_HD PoleState advance_pole(const EnvParams& p, const PoleState& s, int32_t action) {
+//
+// cos(theta) / sin(theta) of the CURRENT state are passed in: the reference evaluates them four times per step
+// (cartpole.py:44-45 for the dynamics, :141 for the reward, :172-173 for the observation) on two distinct angles;
+// the lane keeps the pair for its current angle (SinCos below), so each step computes them once.
+struct SinCos { double sn, cs; };
+BSB_HD SinCos sincos_of(double theta) {
+  SinCos r;
+#if defined(__CUDA_ARCH__)
+  sincos(theta, &r.sn, &r.cs);
+#else
+  r.sn = sin(theta); r.cs = cos(theta);       // the host path calls libm exactly like numpy does
+#endif
+  return r;
+}
+
+BSB_HD PoleState advance_pole(const EnvParams& p, const PoleState& s, const SinCos& trig, int32_t action) {
   const double force = (double)(action - 1) * p.cp_force_mag;
-  const double c = cos(s.theta), sn = sin(s.theta);
+  const double c = trig.cs, sn = trig.sn;
   const double temp = (force + p.cp_pl * square_like_reference(s.theta_dot) * sn) / p.cp_mass_total;
   const double theta_acc = (p.cp_gravity * sn - c * temp) /
       (p.cp_length * (p.cp_four_thirds - p.cp_mass_pole * square_like_reference(c) / p.cp_mass_total));
@@ -218,7 +233,7 @@ struct CartpoleT {
   static const bool kIsDeepSea = false;
   // obs: 6 (cartpole.py:167-177) or 8 (cartpole_swingup.py:137-150) floats
   enum { kObs = kSwingup ? 8 : 6, kInfo = kSwingup ? 3 : 2 };
-  struct Lane { PoleState s; double episode_return, raw_return; uint32_t nr; };
+  struct Lane { PoleState s; SinCos trig; double episode_return, raw_return; uint32_t nr; };
 
   static BSB_HD void load(const EnvParams& p, int64_t i, Lane& L) {
     const int64_t B = p.batch;
@@ -227,6 +242,7 @@ struct CartpoleT {
     L.episode_return = p.st_f64[5 * B + i];
     L.raw_return = p.info[i];
     L.nr = p.st_word[i] >> 31;
+    L.trig = sincos_of(L.s.theta);
   }
   static BSB_HD void store(const EnvParams& p, int64_t i, const Lane& L) {
     const int64_t B = p.batch;
@@ -238,6 +254,7 @@ struct CartpoleT {
   }
   static BSB_HD void init(const EnvParams&, Lane& L) {
     L.s.x = L.s.x_dot = L.s.theta = L.s.theta_dot = L.s.t = 0.0;   // cartpole.py:89
+    L.trig.sn = 0.0; L.trig.cs = 1.0;
     L.episode_return = 0.0; L.raw_return = 0.0; L.nr = 1;
   }
   template <class R> static BSB_HD void ctor_draws(const EnvParams&, Lane&, R&) {}
@@ -250,18 +267,20 @@ struct CartpoleT {
     L.s.theta = kSwingup ? (3.141592653589793 + th) : th;
     L.s.theta_dot = rng.uniform(-p.init_range, p.init_range);
     L.s.t = 0.0;
+    L.trig = sincos_of(L.s.theta);
     L.episode_return = 0.0;
     return make_first();
   }
   template <class R> static BSB_HD StepOut step(const EnvParams& p, int64_t i, Lane& L, int32_t action, R&) {
-    L.s = advance_pole(p, L.s, action);
+    L.s = advance_pole(p, L.s, L.trig, action);
+    L.trig = sincos_of(L.s.theta);
     double reward; bool done;
     if (!kSwingup) {                                       // cartpole.py:140-153
-      const bool ok = cos(L.s.theta) > p.height_threshold && fabs(L.s.x) < p.x_threshold;
+      const bool ok = L.trig.cs > p.height_threshold && fabs(L.s.x) < p.x_threshold;
       reward = ok ? 1.0 : 0.0;
       done = (L.s.t > p.max_time) || !ok;
     } else {                                               // cartpole_swingup.py:104-123
-      const bool upright = cos(L.s.theta) > p.height_threshold &&
+      const bool upright = L.trig.cs > p.height_threshold &&
                            fabs(L.s.theta_dot) < p.theta_dot_threshold &&
                            fabs(L.s.x) < p.x_reward_threshold;
       const int32_t moved = action - 1 < 0 ? 1 - action : action - 1;
@@ -282,8 +301,8 @@ struct CartpoleT {
   static BSB_HD void row(const EnvParams& p, const Lane& L, float* dst, int64_t stride) {
     dst[0 * stride] = (float)(L.s.x / p.x_threshold);
     dst[1 * stride] = (float)(L.s.x_dot / p.x_threshold);
-    dst[2 * stride] = (float)sin(L.s.theta);
-    dst[3 * stride] = (float)cos(L.s.theta);
+    dst[2 * stride] = (float)L.trig.sn;
+    dst[3 * stride] = (float)L.trig.cs;
     dst[4 * stride] = (float)L.s.theta_dot;
     dst[5 * stride] = (float)(L.s.t / p.max_time);
     if (kSwingup) {

@@ -27,6 +27,9 @@ def _np(t):
     ('memory_chain', dict(memory_length=3, num_bits=64), 9),    # maximum context width
     ('discounting_chain', dict(mapping_seed=1), 65),
     ('bandit', dict(mapping_seed=5), 31),
+    ('umbrella_chain', dict(chain_length=3, n_distractor=300), 70),   # 303-float rows: 77 KB stage per warp
+    ('catch', dict(rows=20, columns=20), 50),                        # 400-float boards: 102 KB stage per warp
+    ('deep_sea', dict(size=100, mapping_seed=2), 40),                # 40 KB tiles: beyond the staged bulk path
 ])
 def test_rollout_with_device_sampled_actions_matches_oracle(device, env_class, kwargs, batch):
   """Actions sampled ON DEVICE by the Philox action stream; `random_actions` is the host mirror; the whole
