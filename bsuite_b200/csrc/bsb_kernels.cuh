@@ -15,12 +15,13 @@
 //   * catch: the same stage holds the warp's 32 boards and stays ZERO between
 //     steps; each thread only un-pokes its two old cells and pokes its two new
 //     ones before the elected lane issues the bulk store of all 32 boards.
-//   * deep_sea (N x N one-hot tile per lane, 4 KB at N = 32): default path is
-//     16-byte streaming stores -- the warp walks its 32 lanes and all threads write
-//     each lane's contiguous tile, the hot cell chosen per float4 from a descriptor
-//     broadcast by __shfl_sync.  Alternative path (emit_bulk): a per-warp ring of 4
-//     zeroed tiles in shared memory; the elected lane pokes the hot cell of the next
-//     free tile and issues one bulk store per lane tile.
+//   * deep_sea (N x N one-hot tile per lane, 4 KB at N = 32): per warp two staging buffers of m zeroed tiles
+//     (m = 8 at N = 32); the threads of a group poke their lanes' hot cells (un-poking what they poked into that
+//     buffer two stores ago) and the elected lane issues ONE bulk store of the m contiguous tiles (32 KB).
+//     Large stores matter: the TMA unit costs ~70 ns + bytes / 64 GB/s per SM, so 4 KB stores cap the chip at
+//     ~4.6 TB/s while 32 KB stores reach the HBM write ceiling.  Unaligned tiles (odd N) use 16-byte streaming
+//     stores instead: the warp walks its lanes, every thread writes part of each lane's tile, the hot cell
+//     chosen per float4 from a descriptor broadcast by __shfl_sync.
 //   * mnist: gathered int8 image -> float32 tile, 16-byte stores.
 //
 // A launch covers T consecutive steps with lane state held in registers (T = 1
@@ -276,13 +277,14 @@ template <> struct Descriptor<Mnist> {
 //   * default launch: one chunk per warp, ceil(B / 32) warps; small CTAs (64 threads) keep the per-SM share of
 //     the 2048 chunks of a 65 536-lane batch within ~1% of even on 148 SMs and let the hardware CTA scheduler
 //     balance SMs dynamically.
-//   * deep_sea bulk path: a PERSISTENT grid (as many warps as fit the SMs' shared memory) whose warps pull chunk
-//     indices from a global counter (atomicAdd by the elected lane, one fetch kept in flight ahead of use).  SMs
-//     drain HBM at slightly different rates (L2 slice / die distance), so dynamic dealing matters: a static
-//     equal split measured 15% slower.  A warp loads its next chunk's state while the TMA unit is still draining
-//     the previous chunk's stores.  The counter is never reset: launch k starts at work_base_k =
-//     work_base_(k-1) + chunks + 2 * warps of launch k-1 (every warp makes exactly two failing fetches: the one
-//     that ends its loop and the one already in flight behind it).
+//   * deep_sea bulk path: a PERSISTENT grid (as many warps as fit the SMs' shared memory: 3 per SM at N = 32)
+//     whose warps pull chunk indices from a global counter (atomicAdd by the elected lane).  SMs drain HBM at
+//     slightly different rates (L2 slice / die distance), so dynamic dealing matters -- and so does not reserving
+//     work early: measured on one box, static equal split 48.0 us/step, two fetches ahead 48.0, one ahead 45.5,
+//     LAZY (fetch only after the current chunk's stores are issued; fetch_ahead == 2, the default) 43.9.  The
+//     TMA unit keeps draining the warp's last two stores while it fetches and loads the next chunk's state.
+//     The counter is never reset: launch k starts at work_base_k = work_base_(k-1) + chunks + f * warps of
+//     launch k-1, f = failing fetches per warp (1, or 2 with two fetches ahead).
 template <class F, int RK, bool kNoise, bool kTrack>
 __global__ void __launch_bounds__(128) transition_kernel(const EnvParams p, const LaunchArgs a) {
   typedef typename RngOf<RK>::type R;
@@ -310,9 +312,9 @@ __global__ void __launch_bounds__(128) transition_kernel(const EnvParams p, cons
   const int CH = a.chunk_lanes;
   const int64_t n_chunks = (B + CH - 1) / CH;
   const bool dynamic = a.work_counter != nullptr;
-  // Dynamic dealing keeps TWO fetches ahead of use: the elected lane issues an atomicAdd and only broadcasts its
-  // result one chunk later, so neither the atomic round trip nor (below) the next chunk's action loads -- which
-  // may come from pinned HOST memory over PCIe in the zero-copy bsb_step_host path -- sit on the critical path.
+  // Chunk reservation policy (fetch_ahead): 2 = lazy (default), 0 = reserve the next chunk at the top of the
+  // current one, 1 = keep two fetches in flight and prefetch the next chunk's actions (helps latency, hurts
+  // balance: measured slower).  The elected lane issues the atomicAdd; the result is broadcast with a shuffle.
   unsigned long long pending = 0;                // elected lane: result of the fetch in flight
   auto issue_fetch = [&]() { if (tid == 0) pending = atomicAdd(a.work_counter, 1ull) - a.work_base; };
   auto collect_fetch = [&]() -> int64_t { return (int64_t)__shfl_sync(0xffffffffu, pending, 0); };

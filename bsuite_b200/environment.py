@@ -108,8 +108,15 @@ class StepBuffers:
     self.discount = discount
     self.step_type = step_type
     self.actions = actions
+    self._outputs = None      # struct bsb_outputs over these tensors, built once (the tensors are never swapped)
+    self._timestep = None
 
   def as_outputs(self) -> _lib.Outputs:
+    if self._outputs is None:
+      self._outputs = self._build_outputs()
+    return self._outputs
+
+  def _build_outputs(self) -> _lib.Outputs:
     import torch
     out = _lib.Outputs()
     if self.observation is not None:
@@ -126,8 +133,10 @@ class StepBuffers:
     return out
 
   def timestep(self) -> 'dm_env.TimeStep':
-    return dm_env.TimeStep(step_type=self.step_type, reward=self.reward, discount=self.discount,
-                           observation=self.observation)
+    if self._timestep is None:
+      self._timestep = dm_env.TimeStep(step_type=self.step_type, reward=self.reward, discount=self.discount,
+                                       observation=self.observation)
+    return self._timestep
 
 
 class BatchedEnvironment:
@@ -195,7 +204,10 @@ class BatchedEnvironment:
   def _stream(self):
     if self._ordinal < 0:
       return None
-    return ctypes.c_void_p(self._torch.cuda.current_stream(self._device).cuda_stream)
+    raw = getattr(self._torch._C, '_cuda_getCurrentRawStream', None)   # the cudaStream_t as an int, no wrapper object
+    if raw is not None:
+      return raw(self._ordinal)
+    return self._torch.cuda.current_stream(self._device).cuda_stream
 
   def _device_actions(self, actions, shape):
     torch = self._torch
@@ -217,11 +229,15 @@ class BatchedEnvironment:
 
   def step(self, actions, out: Optional[StepBuffers] = None):
     """base.Environment.step for every lane (base.py:59-65); actions int [B]."""
-    actions = self._device_actions(actions, (self._batch,))
-    out = out or self.make_buffers()
-    outputs = out.as_outputs()
-    _lib.check(self._lib.bsb_step(self._handle.ptr, ctypes.c_void_p(actions.data_ptr()), ctypes.byref(outputs),
-                                  self._stream()))
+    torch = self._torch
+    if not (type(actions) is torch.Tensor and actions.dtype is torch.int32 and actions.device == self._device
+            and actions.dim() == 1 and actions.shape[0] == self._batch and actions.is_contiguous()):
+      actions = self._device_actions(actions, (self._batch,))
+    if out is None:
+      out = self.make_buffers()
+    status = self._lib.bsb_step(self._handle.ptr, actions.data_ptr(), ctypes.byref(out.as_outputs()), self._stream())
+    if status:
+      _lib.check(status)
     return out.timestep()
 
   def make_host_buffers(self, with_observation: bool = False) -> StepBuffers:

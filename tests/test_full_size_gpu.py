@@ -142,3 +142,25 @@ def test_deep_sea_bulk_path_equals_vector_path_at_scale(bsuite_id, batch, monkey
     env.close()
   for a, b in zip(*results):
     assert torch.equal(a, b)
+
+
+def test_mixed_float_dynamics_batch():
+  """BASELINE config #4 as ONE heterogeneous batch: 131 072 cartpole lanes + 131 072 mountain_car lanes advanced
+  together by SweepBatch (each family's fused rollout on its own stream); fp tolerance 1e-6 on sampled lanes."""
+  from bsuite_b200 import suite
+  lanes, T, seed = 131072, 120, 17
+  batch = suite.SweepBatch(['cartpole/0', 'mountain_car/0'], lanes=lanes, device='cuda', seed=seed)
+  result = batch.rollout(T, action_seed=5)
+  torch.cuda.synchronize()
+  for bsuite_id, env_class in (('cartpole/0', 'cartpole'), ('mountain_car/0', 'mountain_car')):
+    ts = result[bsuite_id]
+    assert tuple(ts.observation.shape)[:2] == (T, lanes) and bool(torch.isfinite(ts.observation).all())
+    actions = batch._buffers[bsuite_id].actions.cpu().numpy()   # pylint: disable=protected-access
+    for lane in _sample_lanes(lanes, count=12):
+      want = oracle.run_lanes(env_class, {}, actions[:, lane:lane + 1], seed=seed, lane_offset=int(lane))
+      np.testing.assert_array_equal(ts.step_type[:, lane].cpu().numpy(), want['step_type'][:, 0])
+      np.testing.assert_allclose(ts.reward[:, lane].cpu().numpy(), want['reward'][:, 0], rtol=0, atol=1e-6)
+      np.testing.assert_allclose(ts.observation[:, lane].cpu().numpy(), want['observation'][:, 0], rtol=0, atol=1e-6)
+  returns = batch.gather_returns()
+  assert tuple(returns.shape) == (1, 2, 3) and float(returns[0, 1, 0]) < 0 < float(returns[0, 0, 0])
+  batch.close()
