@@ -362,7 +362,7 @@ def engine_main(args):
     line = {
         'metric': METRIC, 'value': value, 'unit': 'env-steps/s', 'n_gpus': world, 'steps': K, 'warmup': W,
         'ms_per_step': total_ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f64', 'data': 'synthetic',
+        'dtype': 'u32 lane state, f64 reward, f32 observation', 'data': 'synthetic',
         'config': {'workload': f'deep_sea size={SIZE} batch={B} per GPU ({BSUITE_ID}), uniform random actions',
                    'bsuite_id': BSUITE_ID, 'batch_per_gpu': B, 'global_batch': world * B,
                    'parallelism': f'lanes sharded over {world} GPU(s), no data-path collective; one all-gather of '
@@ -379,7 +379,10 @@ def engine_main(args):
         'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 4 * B, 'd2h_bytes_per_step': 12 * B,
                 'steps': Ke, 'host_obs_value': host_obs_value,
                 'host_obs_d2h_bytes_per_step': 4 * B * SIZE * SIZE + 12 * B,
-                'note': 'value: observations stay on the device (the API contract); host_obs_value also copies them out'},
+                'note': 'BatchedEnvironment.step_host -> bsb_step_host every step: actions come from pinned host memory and '
+                        'reward/discount/step_type land in pinned host memory (read / written in place over PCIe by the '
+                        'kernel: zero-copy), then a stream synchronise; observations stay on the device (the API '
+                        'contract). host_obs_value also copies the observations to pinned host memory every step.'},
         'gpu_launches': int(launches),
         'fused_rollout': fused,
         'clocks': clocks,

@@ -38,9 +38,18 @@ def _check_timestep(env, ts, first):
     assert ts.discount == (0.0 if ts.last() else 1.0)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize('bsuite_id', ['deep_sea/2', 'catch_noise/0', 'cartpole/0', 'memory_size/3', 'mnist/0'])
+def test_dm_env_contract_on_cuda(bsuite_id, mnist_dir):
+  _contract(bsuite_b200.load_from_id(bsuite_id, seed=3), bsuite_id)     # default device: cuda
+
+
 @pytest.mark.parametrize('bsuite_id', _CONFORMANCE_IDS)
 def test_dm_env_contract(bsuite_id, mnist_dir):
-  env = bsuite_b200.load_from_id(bsuite_id, device='cpu', seed=3)
+  _contract(bsuite_b200.load_from_id(bsuite_id, device='cpu', seed=3), bsuite_id)
+
+
+def _contract(env, bsuite_id):
   assert isinstance(env, dm_env.Environment)
   assert env.bsuite_num_episodes == sweep.EPISODES[bsuite_id] > 0
   spec = env.action_spec()
@@ -81,18 +90,27 @@ def _known_answers():
   return json.load(open(os.path.join(cf.GOLDEN_DIR, 'known_answers.json')))
 
 
+DEVICES = [pytest.param('cpu', id='host'), pytest.param('cuda', id='cuda', marks=pytest.mark.gpu)]
+
+
+@pytest.mark.parametrize('device', DEVICES)
 @pytest.mark.parametrize('row', _known_answers(), ids=lambda r: r['label'][:40])
-def test_adapter_reproduces_unpatched_reference(row):
+def test_adapter_reproduces_unpatched_reference(row, device):
   """`load_from_id(id)` / `make(cls, seed=int)` with the default MT19937 stream vs the SURVEY.md 8c table:
   reset() + 1000 step() calls digest, #LAST and bsuite_info() of the unmodified reference with the same seed.
   BASELINE config #1 is the first row (deep_sea/0: digest 07810643f8b8dcfc, 91 episodes)."""
   if row['kind'] == 'load_from_id':
-    env = bsuite_b200.load_from_id(row['bsuite_id'], device='cpu')
+    env = bsuite_b200.load_from_id(row['bsuite_id'], device=device)
   else:
-    env = bsuite_b200.make(row['env_class'], device='cpu', **row['kwargs'])
+    env = bsuite_b200.make(row['env_class'], device=device, **row['kwargs'])
   actions = np.random.RandomState(0).randint(env.action_spec().num_values, size=1000)
   rows = [env.reset()] + [env.step(int(a)) for a in actions]
   float_family = row.get('env_class') in cf.FLOAT_FAMILIES
+  if device == 'cuda' and (float_family or (row.get('env_class') == 'deep_sea' and not row['kwargs'].get('deterministic', True))):
+    # CUDA sin/cos/log are not glibc's: same trajectory within tolerance, not the same digest
+    assert sum(ts.last() for ts in rows) == row['num_last']
+    assert sum(ts.reward or 0.0 for ts in rows) == pytest.approx(row['reward_sum'], abs=1e-6)
+    return
   assert sum(ts.last() for ts in rows) == row['num_last']
   info = {k: float(v) for k, v in env.bsuite_info().items()}
   if float_family:
