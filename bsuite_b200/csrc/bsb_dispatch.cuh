@@ -88,8 +88,7 @@ int device_launch(bsb_env* e, LaunchArgs a, cudaStream_t stream) {
   a.group_lanes = 1;
   a.work_counter = nullptr;
   a.work_base = 0;
-  a.fetch_ahead = e->fetch_ahead;
-  a.chunk_lanes = 32;
+  a.lazy_fetch = e->lazy_fetch;
   int threads = e->block_threads;
   bool persistent = false;
   if (is_onehot && a.emit_bulk) {
@@ -114,15 +113,14 @@ int device_launch(bsb_env* e, LaunchArgs a, cudaStream_t stream) {
   if (smem > 48 * 1024) BSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t grid = (B + threads - 1) / threads;
   if (persistent) {
-    // As many CTAs as are co-resident (shared-memory bound; 1 KB per CTA is reserved by the driver); each warp
-    // then owns a contiguous, equally sized range of lanes.
+    // As many CTAs as are co-resident (shared-memory bound; 1 KB per CTA is reserved by the driver); their warps
+    // draw 32-lane chunks from the environment's global counter.
     const int64_t per_sm = (int64_t)((227 * 1024) / (smem + 1024));
     const int64_t resident = (int64_t)e->num_sms * (per_sm < 1 ? 1 : (per_sm > 16 ? 16 : per_sm));
     if (grid > resident) {
       grid = resident;
       a.work_counter = e->work_counter;
       a.work_base = e->work_base;
-      if (e->deep_sea_chunk == 16 && a.group_lanes <= 16) a.chunk_lanes = 16;
     } else {
       persistent = false;      // everything is resident anyway: one chunk per warp
     }
@@ -141,7 +139,8 @@ int device_launch(bsb_env* e, LaunchArgs a, cudaStream_t stream) {
     cfg.numAttrs = 1;
   }
   BSB_CUDA(cudaLaunchKernelEx(&cfg, kernel, e->p, a));
-  if (a.work_counter) e->work_base += (unsigned long long)((B + a.chunk_lanes - 1) / a.chunk_lanes) + (a.fetch_ahead == 1 ? 2ull : 1ull) * (unsigned long long)grid * (unsigned long long)(threads / 32);
+  // every chunk is fetched once and every warp makes exactly one failing fetch
+  if (a.work_counter) e->work_base += (unsigned long long)((B + 31) / 32) + (unsigned long long)grid * (unsigned long long)(threads / 32);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return BSB_OK;
 }

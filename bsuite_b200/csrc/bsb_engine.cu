@@ -225,8 +225,7 @@ int32_t bsb_create(const bsb_config* config, int64_t batch, int32_t device, uint
     e->use_pdl = flag("BSB_PDL", 1);
     e->deep_sea_persistent = flag("BSB_DEEP_SEA_PERSISTENT", 1);
     e->zero_copy = flag("BSB_ZERO_COPY", 1);
-    { const char* v = getenv("BSB_FETCH_AHEAD"); e->fetch_ahead = v ? atoi(v) : 2; if (e->fetch_ahead < 0 || e->fetch_ahead > 2) e->fetch_ahead = 2; }
-    { const char* v = getenv("BSB_DEEP_SEA_CHUNK"); e->deep_sea_chunk = (v && atoi(v) == 16) ? 16 : 32; }
+    e->lazy_fetch = flag("BSB_LAZY_FETCH", 1);
     e->work_counter = nullptr; e->work_base = 0;
     e->num_sms = 148;
     if (device >= 0) { int n = 0; if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && n > 0) e->num_sms = n; }

@@ -42,8 +42,7 @@ struct bsb_env {
   unsigned long long work_base;      // its value when the next launch starts
   int use_pdl;            // programmatic dependent launch between consecutive steps
   int zero_copy;          // bsb_step_host: kernel reads/writes pinned host buffers directly
-  int fetch_ahead;        // persistent kernel: chunk reservation policy (0 one ahead, 1 two ahead, 2 lazy)
-  int deep_sea_chunk;     // lanes per chunk of the persistent deep_sea path (32 or 16)
+  int lazy_fetch;         // persistent kernel: fetch the next chunk lazily (default) or one chunk ahead
   int num_sms;
   bsb::InfoNames names;
   std::vector<void*> allocs;

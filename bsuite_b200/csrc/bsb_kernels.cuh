@@ -50,9 +50,7 @@ struct LaunchArgs {
   int32_t emit_bulk;        // use TMA bulk stores where the emitter supports them
   int32_t use_pdl;          // launched with programmatic stream serialization
   int32_t group_lanes;      // deep_sea bulk path: lanes per bulk store (power of two, 1..32)
-  int32_t fetch_ahead;      // persistent launches: chunk reservation policy (0 one ahead, 1 two ahead, 2 lazy)
-  int32_t chunk_lanes;      // lanes per chunk (32; the deep_sea persistent path may use 16 for a finer tail)
-  int32_t reserved;
+  int32_t lazy_fetch;       // persistent launches: 1 = fetch the next chunk only when the current one is issued
   unsigned long long* work_counter;  // persistent launches: monotonically increasing chunk counter (device)
   unsigned long long work_base;      // value of *work_counter at which this launch's chunk 0 starts
 };
@@ -208,22 +206,33 @@ __device__ __forceinline__ void emit_twohot_vec(float* obs_t, int64_t warp_base,
   }
 }
 
-// Image tiles gathered from the int8 dataset (`image` < 0: zeros).
+// Image tiles gathered from the int8 dataset (`image` < 0: zeros).  The gather is latency-bound if each
+// load -> convert -> store chain runs serially, so all loads of a lane's tile (up to 8 x 32 char4 = 1 024 pixels
+// per pass) are issued before the first conversion.
 __device__ __forceinline__ void emit_image(const EnvParams& p, float* obs_t, int64_t warp_base, int n_lanes, int K, int image, bool vec) {
   const int tid = threadIdx.x & 31;
+  constexpr int U = 8;
   for (int j = 0; j < n_lanes; ++j) {
     const int img = __shfl_sync(0xffffffffu, image, j);
     float* dst = obs_t + (warp_base + j) * (int64_t)K;
     const int8_t* src = p.images + (int64_t)(img < 0 ? 0 : img) * K;
     if (vec) {
       const int K4 = K >> 2;
-      for (int q = tid; q < K4; q += 32) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (img >= 0) {
-          const char4 c = __ldg(reinterpret_cast<const char4*>(src) + q);
-          v = make_float4(Mnist::pixel(c.x), Mnist::pixel(c.y), Mnist::pixel(c.z), Mnist::pixel(c.w));
+      const char4* src4 = reinterpret_cast<const char4*>(src);
+      float4* dst4 = reinterpret_cast<float4*>(dst);
+      for (int q0 = 0; q0 < K4; q0 += 32 * U) {
+        char4 c[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int q = q0 + u * 32 + tid;
+          c[u] = make_char4(0, 0, 0, 0);
+          if (img >= 0 && q < K4) c[u] = __ldg(src4 + q);
         }
-        st_stream(reinterpret_cast<float4*>(dst) + q, v);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int q = q0 + u * 32 + tid;
+          if (q < K4) st_stream(dst4 + q, make_float4(Mnist::pixel(c[u].x), Mnist::pixel(c[u].y), Mnist::pixel(c[u].z), Mnist::pixel(c[u].w)));
+        }
       }
     } else {
       for (int e = tid; e < K; e += 32) st_stream(dst + e, img >= 0 ? Mnist::pixel(src[e]) : 0.f);
@@ -281,10 +290,10 @@ template <> struct Descriptor<Mnist> {
 //     whose warps pull chunk indices from a global counter (atomicAdd by the elected lane).  SMs drain HBM at
 //     slightly different rates (L2 slice / die distance), so dynamic dealing matters -- and so does not reserving
 //     work early: measured on one box, static equal split 48.0 us/step, two fetches ahead 48.0, one ahead 45.5,
-//     LAZY (fetch only after the current chunk's stores are issued; fetch_ahead == 2, the default) 43.9.  The
-//     TMA unit keeps draining the warp's last two stores while it fetches and loads the next chunk's state.
-//     The counter is never reset: launch k starts at work_base_k = work_base_(k-1) + chunks + f * warps of
-//     launch k-1, f = failing fetches per warp (1, or 2 with two fetches ahead).
+//     LAZY (fetch only after the current chunk's stores are issued; the default) 43.9.  The TMA unit keeps
+//     draining the warp's last two stores while it fetches and loads the next chunk's state.  The counter is
+//     never reset: launch k starts at work_base_k = work_base_(k-1) + chunks + warps of launch k-1 (every warp
+//     makes exactly one failing fetch).
 template <class F, int RK, bool kNoise, bool kTrack>
 __global__ void __launch_bounds__(128) transition_kernel(const EnvParams p, const LaunchArgs a) {
   typedef typename RngOf<RK>::type R;
@@ -309,22 +318,16 @@ __global__ void __launch_bounds__(128) transition_kernel(const EnvParams p, cons
   // to become resident: its CTAs park at their own wait, so at most one dependent grid is ever pending.
   if (a.use_pdl) { pdl_wait(); pdl_launch_dependents(); }
 
-  const int CH = a.chunk_lanes;
-  const int64_t n_chunks = (B + CH - 1) / CH;
+  const int64_t n_chunks = (B + 31) / 32;
   const bool dynamic = a.work_counter != nullptr;
-  // Chunk reservation policy (fetch_ahead): 2 = lazy (default), 0 = reserve the next chunk at the top of the
-  // current one, 1 = keep two fetches in flight and prefetch the next chunk's actions (helps latency, hurts
-  // balance: measured slower).  The elected lane issues the atomicAdd; the result is broadcast with a shuffle.
-  unsigned long long pending = 0;                // elected lane: result of the fetch in flight
-  auto issue_fetch = [&]() { if (tid == 0) pending = atomicAdd(a.work_counter, 1ull) - a.work_base; };
-  auto collect_fetch = [&]() -> int64_t { return (int64_t)__shfl_sync(0xffffffffu, pending, 0); };
-  int64_t cur_chunk;
-  const bool ahead = a.fetch_ahead == 1, lazy = a.fetch_ahead == 2;
-  if (dynamic) { issue_fetch(); cur_chunk = collect_fetch(); if (ahead) issue_fetch(); }
-  else cur_chunk = (int64_t)blockIdx.x * warps_per_cta + warp;
-  const bool prefetch_actions = ahead && a.actions != nullptr && a.T == 1 && a.mode == MODE_STEP;
-  int32_t ahead_action = 0;                      // action of lane (cur_chunk * 32 + tid), loaded one chunk early
-  if (prefetch_actions && cur_chunk < n_chunks && tid < CH && cur_chunk * CH + tid < B) ahead_action = a.actions[cur_chunk * CH + tid];
+  const bool lazy = a.lazy_fetch != 0;
+  // The elected lane draws chunk indices from the global counter; the result is broadcast with a shuffle.
+  auto fetch_chunk = [&]() -> int64_t {
+    unsigned long long v = 0;
+    if (tid == 0) v = atomicAdd(a.work_counter, 1ull) - a.work_base;
+    return (int64_t)__shfl_sync(0xffffffffu, v, 0);
+  };
+  int64_t cur_chunk = dynamic ? fetch_chunk() : (int64_t)blockIdx.x * warps_per_cta + warp;
 
   const bool has_rng = p.rng_pos != nullptr;
   // catch: cells this thread poked into stage buffer 0 / 1 (cleared when that buffer is reused)
@@ -335,13 +338,10 @@ __global__ void __launch_bounds__(128) transition_kernel(const EnvParams p, cons
   bool any_bulk = false;
 
   while (cur_chunk < n_chunks) {
-    const int64_t warp_base = cur_chunk * CH;
-    const int32_t my_action = ahead_action;
-    if (dynamic && !ahead && !lazy) issue_fetch();         // default: reserve the next chunk now (one chunk ahead)
-    cur_chunk = (dynamic && !lazy) ? collect_fetch() : n_chunks;   // ahead: this fetch was issued a chunk ago
-    if (dynamic && ahead) issue_fetch();
-    if (prefetch_actions && cur_chunk < n_chunks && tid < CH && cur_chunk * CH + tid < B) ahead_action = a.actions[cur_chunk * CH + tid];
-    const int n_lanes = (B - warp_base) < CH ? (int)(B - warp_base) : CH;
+    const int64_t warp_base = cur_chunk * 32;
+    // eager policy: reserve the next chunk now; lazy (default): only after this chunk's stores are issued
+    cur_chunk = (dynamic && !lazy) ? fetch_chunk() : n_chunks;
+    const int n_lanes = (B - warp_base) < 32 ? (int)(B - warp_base) : 32;
     const int64_t lane = warp_base + tid;
     const bool active = tid < n_lanes;
     // Bulk (TMA) emission needs 16-byte aligned spans; the choice is warp-uniform per chunk.
@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(128) transition_kernel(const EnvParams p, cons
         F::store(p, lane, L);
         if (has_rng) rng_close(rng, p, lane, false);
       }
-      if (dynamic && lazy) { issue_fetch(); cur_chunk = collect_fetch(); }
+      if (dynamic && lazy) cur_chunk = fetch_chunk();
       continue;
     }
 
@@ -381,9 +381,8 @@ __global__ void __launch_bounds__(128) transition_kernel(const EnvParams p, cons
       if (active) {
         int32_t action = 0;
         if (a.mode == MODE_STEP) {
-          action = prefetch_actions ? my_action
-                 : (a.actions ? a.actions[off]
-                              : action_stream.sample(a.action_seed, p.lane_offset + (uint64_t)lane, (uint64_t)(a.step0 + t), p.num_actions));
+          action = a.actions ? a.actions[off]
+                             : action_stream.sample(a.action_seed, p.lane_offset + (uint64_t)lane, (uint64_t)(a.step0 + t), p.num_actions);
           if (a.actions_out) a.actions_out[off] = action;
         }
         const StepOut o = lane_transition<F, R, R>(p, lane, L, rng, wrng, action, a.mode, kNoise);
@@ -472,7 +471,7 @@ __global__ void __launch_bounds__(128) transition_kernel(const EnvParams p, cons
       if (kNoise) rng_close(wrng, p, lane, true);
       if (kTrack) ep.store(p, lane);
     }
-    if (dynamic && lazy) { issue_fetch(); cur_chunk = collect_fetch(); }   // lazy: nothing reserved while working
+    if (dynamic && lazy) cur_chunk = fetch_chunk();        // lazy: nothing was reserved while working
   }
   if (any_bulk && tid == 0) bulk_wait_read<0>();      // shared memory must outlive the last bulk read
 }
