@@ -127,6 +127,7 @@ __host__ __device__
 size_t smem_floats_per_warp(int K, bool emit_bulk, int group_lanes) {
   if (EmitKind<F>::value == EMIT_ROWS || EmitKind<F>::value == EMIT_TWOHOT) return (size_t)ROW_STAGES * 32 * (size_t)K;
   if (EmitKind<F>::value == EMIT_ONEHOT && emit_bulk) return (size_t)TILE_STAGES * (size_t)group_lanes * (size_t)K;
+  if (EmitKind<F>::value == EMIT_IMAGE) return 256;        // int8 pixel -> float32 lookup table
   return 0;
 }
 
@@ -206,10 +207,11 @@ __device__ __forceinline__ void emit_twohot_vec(float* obs_t, int64_t warp_base,
   }
 }
 
-// Image tiles gathered from the int8 dataset (`image` < 0: zeros).  The gather is latency-bound if each
-// load -> convert -> store chain runs serially, so all loads of a lane's tile (up to 8 x 32 char4 = 1 024 pixels
-// per pass) are issued before the first conversion.
-__device__ __forceinline__ void emit_image(const EnvParams& p, float* obs_t, int64_t warp_base, int n_lanes, int K, int image, bool vec) {
+// Image tiles gathered from the int8 dataset (`image` < 0: zeros).  `lut` is the warp's 256-entry table of
+// (float)(int8)i / 255 in shared memory: IEEE float division costs ~10 instructions and takes a slow path for zero
+// numerators (most MNIST pixels), a table lookup costs one LDS.  The gather is latency-bound if each load ->
+// convert -> store chain runs serially, so all loads of a pass (8 x 32 char4 = 1 024 pixels) are issued first.
+__device__ __forceinline__ void emit_image(const EnvParams& p, const float* lut, float* obs_t, int64_t warp_base, int n_lanes, int K, int image, bool vec) {
   const int tid = threadIdx.x & 31;
   constexpr int U = 8;
   for (int j = 0; j < n_lanes; ++j) {
@@ -218,24 +220,28 @@ __device__ __forceinline__ void emit_image(const EnvParams& p, float* obs_t, int
     const int8_t* src = p.images + (int64_t)(img < 0 ? 0 : img) * K;
     if (vec) {
       const int K4 = K >> 2;
-      const char4* src4 = reinterpret_cast<const char4*>(src);
+      const uchar4* src4 = reinterpret_cast<const uchar4*>(src);
       float4* dst4 = reinterpret_cast<float4*>(dst);
+      if (img < 0) {
+        for (int q = tid; q < K4; q += 32) st_stream(dst4 + q, make_float4(0.f, 0.f, 0.f, 0.f));
+        continue;
+      }
       for (int q0 = 0; q0 < K4; q0 += 32 * U) {
-        char4 c[U];
+        uchar4 c[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int q = q0 + u * 32 + tid;
-          c[u] = make_char4(0, 0, 0, 0);
-          if (img >= 0 && q < K4) c[u] = __ldg(src4 + q);
+          c[u] = make_uchar4(0, 0, 0, 0);
+          if (q < K4) c[u] = __ldg(src4 + q);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int q = q0 + u * 32 + tid;
-          if (q < K4) st_stream(dst4 + q, make_float4(Mnist::pixel(c[u].x), Mnist::pixel(c[u].y), Mnist::pixel(c[u].z), Mnist::pixel(c[u].w)));
+          if (q < K4) st_stream(dst4 + q, make_float4(lut[c[u].x], lut[c[u].y], lut[c[u].z], lut[c[u].w]));
         }
       }
     } else {
-      for (int e = tid; e < K; e += 32) st_stream(dst + e, img >= 0 ? Mnist::pixel(src[e]) : 0.f);
+      for (int e = tid; e < K; e += 32) st_stream(dst + e, img >= 0 ? lut[(uint8_t)src[e]] : 0.f);
     }
   }
 }
@@ -294,8 +300,22 @@ template <> struct Descriptor<Mnist> {
 //     draining the warp's last two stores while it fetches and loads the next chunk's state.  The counter is
 //     never reset: launch k starts at work_base_k = work_base_(k-1) + chunks + warps of launch k-1 (every warp
 //     makes exactly one failing fetch).
+// Register budget per family (second __launch_bounds__ argument, counted in 128-thread blocks per SM).  The
+// generic kernel is register-hungry (two Philox streams, action stream, accumulators); left alone ptxas takes
+// 160-220 registers and 64-thread CTAs then run at 8 warps/SM, which starves the latency-bound small families.
+// Measured on B200 (rollout us/step at 128 vs ~220 registers): cartpole 5.3 vs 8.1, mountain_car 2.6 vs 4.2,
+// umbrella_length 12.7 vs 19.7, memory_len 5.0 vs 7.2; bandit / discounting_chain gain again at <= 64.
+template <class F> struct MinBlocksPerSM { static const int value = 4; };        // <= 128 registers
+template <> struct MinBlocksPerSM<MemoryChain> { static const int value = 6; };   // <= 80
+template <> struct MinBlocksPerSM<Bandit> { static const int value = 8; };        // <= 64
+template <> struct MinBlocksPerSM<DiscountingChain> { static const int value = 8; };
+#ifdef BSB_MIN_BLOCKS_PER_SM   // build-time override for tuning experiments
+#define BSB_LAUNCH_MIN_BLOCKS(F) BSB_MIN_BLOCKS_PER_SM
+#else
+#define BSB_LAUNCH_MIN_BLOCKS(F) MinBlocksPerSM<F>::value
+#endif
 template <class F, int RK, bool kNoise, bool kTrack>
-__global__ void __launch_bounds__(128) transition_kernel(const EnvParams p, const LaunchArgs a) {
+__global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kernel(const EnvParams p, const LaunchArgs a) {
   typedef typename RngOf<RK>::type R;
   constexpr int kEmit = EmitKind<F>::value;
   extern __shared__ float4 smem_raw[];
@@ -312,6 +332,10 @@ __global__ void __launch_bounds__(128) transition_kernel(const EnvParams p, cons
     const int total4 = (int)(stage_floats >> 2);
     for (int q = tid; q < total4; q += 32) s4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int e = (total4 << 2) + tid; e < (int)stage_floats; e += 32) stage[e] = 0.f;
+    __syncwarp();
+  }
+  if (kEmit == EMIT_IMAGE) {      // pixel table: image.astype(float32) / 255 for every int8 value (mnist.py:64)
+    for (int i = tid; i < 256; i += 32) stage[i] = Mnist::pixel((int8_t)(uint8_t)i);
     __syncwarp();
   }
   // Wait for the previous step's kernel (it wrote the lane state read below), THEN allow the next step's kernel
@@ -447,7 +471,7 @@ __global__ void __launch_bounds__(128) transition_kernel(const EnvParams p, cons
           emit_twohot_vec(obs_t, warp_base, n_lanes, K, hot_a, hot_b, vec);
         }
       } else if (kEmit == EMIT_IMAGE) {
-        emit_image(p, obs_t, warp_base, n_lanes, K, Descriptor<F>::a(L), vec && (K & 3) == 0);
+        emit_image(p, stage, obs_t, warp_base, n_lanes, K, Descriptor<F>::a(L), vec && (K & 3) == 0);
       } else {
         float* rows = stage + (size_t)(emitted & 1u) * 32 * K;
         if (bulk) { if (tid == 0) bulk_wait_read<ROW_STAGES - 1>(); }
