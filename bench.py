@@ -101,7 +101,8 @@ def reference_main(args):
   rank = int(os.environ.get('RANK', '0'))
   if rank != 0:
     return 0
-  r = run_reference_sample(args.steps, args.warmup, budget_s=12.0 if args.steps <= 0 else 20.0)
+  budget = float(os.environ.get('BSB_BENCH_BUDGET_S', '12.0' if args.steps <= 0 else '20.0'))
+  r = run_reference_sample(args.steps, args.warmup, budget_s=budget)
   args.steps = r['steps']
   sample = (f"{r['lanes']} of {BATCH_PER_GPU} lanes x {r['steps']} steps, one process per core "
             f"({r['cores']} cores), numpy restatement of bsuite DeepSea.step")
