@@ -139,8 +139,8 @@ int device_launch(bsb_env* e, LaunchArgs a, cudaStream_t stream) {
     cfg.numAttrs = 1;
   }
   BSB_CUDA(cudaLaunchKernelEx(&cfg, kernel, e->p, a));
-  // every chunk is fetched once and every warp makes exactly one failing fetch
-  if (a.work_counter) e->work_base += (unsigned long long)((B + 31) / 32) + (unsigned long long)grid * (unsigned long long)(threads / 32);
+  // chunks [warps, n_chunks) are fetched once each and every warp makes exactly one failing fetch
+  if (a.work_counter) e->work_base += (unsigned long long)((B + 31) / 32);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return BSB_OK;
 }

@@ -51,6 +51,7 @@ struct LaunchArgs {
   int32_t use_pdl;          // launched with programmatic stream serialization
   int32_t group_lanes;      // deep_sea bulk path: lanes per bulk store (power of two, 1..32)
   int32_t lazy_fetch;       // persistent launches: 1 = fetch the next chunk only when the current one is issued
+  int32_t reserved;
   unsigned long long* work_counter;  // persistent launches: monotonically increasing chunk counter (device)
   unsigned long long work_base;      // value of *work_counter at which this launch's chunk 0 starts
 };
@@ -346,12 +347,15 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
   const bool dynamic = a.work_counter != nullptr;
   const bool lazy = a.lazy_fetch != 0;
   // The elected lane draws chunk indices from the global counter; the result is broadcast with a shuffle.
+  // Every warp's FIRST chunk is its own index (no atomic on the start-up path); the counter deals chunks
+  // [total_warps, n_chunks).
+  const int64_t total_warps = (int64_t)gridDim.x * warps_per_cta;
   auto fetch_chunk = [&]() -> int64_t {
     unsigned long long v = 0;
     if (tid == 0) v = atomicAdd(a.work_counter, 1ull) - a.work_base;
-    return (int64_t)__shfl_sync(0xffffffffu, v, 0);
+    return total_warps + (int64_t)__shfl_sync(0xffffffffu, v, 0);
   };
-  int64_t cur_chunk = dynamic ? fetch_chunk() : (int64_t)blockIdx.x * warps_per_cta + warp;
+  int64_t cur_chunk = (int64_t)blockIdx.x * warps_per_cta + warp;
 
   const bool has_rng = p.rng_pos != nullptr;
   // catch: cells this thread poked into stage buffer 0 / 1 (cleared when that buffer is reused)
