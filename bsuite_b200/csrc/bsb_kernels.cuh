@@ -298,9 +298,10 @@ template <> struct Descriptor<Mnist> {
 //     slightly different rates (L2 slice / die distance), so dynamic dealing matters -- and so does not reserving
 //     work early: measured on one box, static equal split 48.0 us/step, two fetches ahead 48.0, one ahead 45.5,
 //     LAZY (fetch only after the current chunk's stores are issued; the default) 43.9.  The TMA unit keeps
-//     draining the warp's last two stores while it fetches and loads the next chunk's state.  The counter is
-//     never reset: launch k starts at work_base_k = work_base_(k-1) + chunks + warps of launch k-1 (every warp
-//     makes exactly one failing fetch).
+//     draining the warp's last two stores while it fetches and loads the next chunk's state.  Every warp's
+//     first chunk is its own index (no atomic on the start-up path); the counter deals the rest and is never
+//     reset: a launch with C chunks and W warps performs exactly C atomicAdds (C - W successful fetches plus one
+//     failing fetch per warp), so launch k starts at work_base_k = work_base_(k-1) + C.
 // Register budget per family (second __launch_bounds__ argument, counted in 128-thread blocks per SM).  The
 // generic kernel is register-hungry (two Philox streams, action stream, accumulators); left alone ptxas takes
 // 160-220 registers and 64-thread CTAs then run at 8 warps/SM, which starves the latency-bound small families.
@@ -346,9 +347,8 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
   const int64_t n_chunks = (B + 31) / 32;
   const bool dynamic = a.work_counter != nullptr;
   const bool lazy = a.lazy_fetch != 0;
-  // The elected lane draws chunk indices from the global counter; the result is broadcast with a shuffle.
-  // Every warp's FIRST chunk is its own index (no atomic on the start-up path); the counter deals chunks
-  // [total_warps, n_chunks).
+  // The elected lane draws chunk indices [total_warps, n_chunks) from the global counter and broadcasts them
+  // with a shuffle; chunk (global warp index) is taken without asking.
   const int64_t total_warps = (int64_t)gridDim.x * warps_per_cta;
   auto fetch_chunk = [&]() -> int64_t {
     unsigned long long v = 0;
