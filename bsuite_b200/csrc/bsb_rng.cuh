@@ -148,6 +148,8 @@ struct PhiloxSrc {
     return (u32)v;
   }
   BSB_HD double next_double() { return (double)(next64() >> 11) * (1.0 / 9007199254740992.0); }
+  // next_double() > 0.5 without floating point: (w >> 11) * 2^-53 > 1/2  <=>  (w >> 11) > 2^52  <=>  w >= 2^63 + 2^11
+  BSB_HD bool next_above_half() { return next64() >= 0x8000000000000800ull; }
 };
 
 // ---------------------------------------------------------------------------
@@ -184,6 +186,11 @@ struct MtSrc {
     const u32 a = next32() >> 5, b = next32() >> 6;
     return ((double)a * 67108864.0 + (double)b) / 9007199254740992.0;
   }
+  // next_double() > 0.5: the numerator a * 2^26 + b is an exact 53-bit integer; compare it with 2^52
+  BSB_HD bool next_above_half() {
+    const u32 a = next32() >> 5, b = next32() >> 6;
+    return (((u64)a << 26) | (u64)b) > (1ull << 52);
+  }
 };
 
 // numpy's legacy seeding of MT19937 from one 32-bit integer.
@@ -212,7 +219,7 @@ struct LegacyRng {
     return low + range * src.next_double();
   }
   // binomial(n=1, p=0.5): inversion with qn = exp(log(0.5)) = 0.5, bound = 1.
-  BSB_HD int binomial_half() { return src.next_double() > 0.5 ? 1 : 0; }
+  BSB_HD int binomial_half() { return src.next_above_half() ? 1 : 0; }
 
   // randint(n) for 1 <= n <= 2^32.
   BSB_HD u32 randint(u32 n) {
