@@ -375,7 +375,7 @@ struct MemoryChain {
 
   template <class R> static BSB_HD void draw_context(const EnvParams& p, Lane& L, R& rng) {
     uint64_t c = 0;                                          // binomial(1, .5, num_bits), row-major
-    for (int b = 0; b < p.num_bits; ++b) c |= (uint64_t)rng.binomial_half() << b;
+    c = rng.binomial_half_bits(p.num_bits);
     L.ctx = c;
     L.query = rng.randint((uint32_t)p.num_bits);
   }
@@ -460,7 +460,11 @@ struct UmbrellaChain {
   template <class R> static BSB_HD void row(const EnvParams& p, const Lane& L, R& rng, float* dst, int64_t stride) {
     dst[0] = (float)L.need; dst[stride] = (float)L.has;
     dst[2 * stride] = (float)(1.0 - (double)L.t / (double)p.chain_length);
-    for (int k = 0; k < p.n_distractor; ++k) dst[(3 + k) * stride] = (float)rng.binomial_half();
+    for (int k0 = 0; k0 < p.n_distractor; k0 += 64) {
+      const int n = (p.n_distractor - k0) < 64 ? (p.n_distractor - k0) : 64;
+      const uint64_t bits = rng.binomial_half_bits(n);
+      for (int k = 0; k < n; ++k) dst[(3 + k0 + k) * stride] = (float)((bits >> k) & 1ull);
+    }
   }
 };
 

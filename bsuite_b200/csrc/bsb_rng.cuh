@@ -150,6 +150,28 @@ struct PhiloxSrc {
   BSB_HD double next_double() { return (double)(next64() >> 11) * (1.0 / 9007199254740992.0); }
   // next_double() > 0.5 without floating point: (w >> 11) * 2^-53 > 1/2  <=>  (w >> 11) > 2^52  <=>  w >= 2^63 + 2^11
   BSB_HD bool next_above_half() { return next64() >= 0x8000000000000800ull; }
+
+  // The next `n` (<= 64) Bernoulli(1/2) draws as bits of the result (draw k -> bit k): binomial(1, .5, size=n).
+  // Once the position is block-aligned, TWO Philox blocks (8 draws) are computed per iteration; the two
+  // ten-round chains are independent, so the scheduler interleaves them and the integer-multiply latency that
+  // bounds a single chain is overlapped (umbrella_chain draws up to 100 of these per lane-step).
+  BSB_HD u64 next_half_bits(int n) {
+    const u64 T = 0x8000000000000800ull;
+    u64 bits = 0;
+    int k = 0;
+    while (k < n && (pos & 3) != 0) { bits |= (u64)next_above_half() << k; ++k; }
+    while (n - k >= 8) {
+      const u64 c = (pos >> 2) + 1;
+      const PhiloxBlock x = philox4x64_10(c, 0, 0, stream, k0, k1);
+      const PhiloxBlock y = philox4x64_10(c + 1, 0, 0, stream, k0, k1);
+      const u64 eight = (u64)(x.v0 >= T) | ((u64)(x.v1 >= T) << 1) | ((u64)(x.v2 >= T) << 2) | ((u64)(x.v3 >= T) << 3) |
+                        ((u64)(y.v0 >= T) << 4) | ((u64)(y.v1 >= T) << 5) | ((u64)(y.v2 >= T) << 6) | ((u64)(y.v3 >= T) << 7);
+      bits |= eight << k;
+      k += 8; pos += 8;
+    }
+    while (k < n) { bits |= (u64)next_above_half() << k; ++k; }
+    return bits;
+  }
 };
 
 // ---------------------------------------------------------------------------
@@ -191,6 +213,11 @@ struct MtSrc {
     const u32 a = next32() >> 5, b = next32() >> 6;
     return (((u64)a << 26) | (u64)b) > (1ull << 52);
   }
+  BSB_HD u64 next_half_bits(int n) {
+    u64 bits = 0;
+    for (int k = 0; k < n; ++k) bits |= (u64)next_above_half() << k;
+    return bits;
+  }
 };
 
 // numpy's legacy seeding of MT19937 from one 32-bit integer.
@@ -220,6 +247,8 @@ struct LegacyRng {
   }
   // binomial(n=1, p=0.5): inversion with qn = exp(log(0.5)) = 0.5, bound = 1.
   BSB_HD int binomial_half() { return src.next_above_half() ? 1 : 0; }
+  // binomial(1, 0.5, size=n), n <= 64, draw k in bit k
+  BSB_HD u64 binomial_half_bits(int n) { return src.next_half_bits(n); }
 
   // randint(n) for 1 <= n <= 2^32.
   BSB_HD u32 randint(u32 n) {
