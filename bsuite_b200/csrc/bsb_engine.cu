@@ -484,8 +484,16 @@ int32_t bsb_step_host(bsb_env* env, const int32_t* actions, const bsb_outputs* h
     void* d_actions = mapped_device_pointer(env, actions);
     void* d_reward = host_out->reward ? mapped_device_pointer(env, host_out->reward) : nullptr;
     void* d_reward64 = host_out->reward_f64 ? mapped_device_pointer(env, host_out->reward_f64) : nullptr;
-    void* d_discount = host_out->discount ? mapped_device_pointer(env, host_out->discount) : nullptr;
-    void* d_step_type = host_out->step_type ? mapped_device_pointer(env, host_out->step_type) : nullptr;
+    void *d_discount = nullptr, *d_step_type = nullptr;
+    const bool packed_scalars = d_reward && host_out->discount == host_out->reward + B &&
+                                reinterpret_cast<char*>(host_out->step_type) == reinterpret_cast<char*>(host_out->reward + 2 * B);
+    if (packed_scalars) {       // reward | discount | step_type back to back in one pinned block: one query covers all
+      d_discount = static_cast<float*>(d_reward) + B;
+      d_step_type = static_cast<float*>(d_reward) + 2 * B;
+    } else {
+      d_discount = host_out->discount ? mapped_device_pointer(env, host_out->discount) : nullptr;
+      d_step_type = host_out->step_type ? mapped_device_pointer(env, host_out->step_type) : nullptr;
+    }
     const bool all_mapped = d_actions && (!host_out->reward || d_reward) && (!host_out->reward_f64 || d_reward64) &&
                             (!host_out->discount || d_discount) && (!host_out->step_type || d_step_type);
     if (all_mapped) {

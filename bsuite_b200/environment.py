@@ -266,32 +266,26 @@ class BatchedEnvironment:
     are also left on the device in `out.observation` for the agent.  Returns (host TimeStep, device observation).
     """
     torch = self._torch
-    if not isinstance(actions, torch.Tensor):
-      actions = torch.as_tensor(np.asarray(actions))
-    if actions.device.type != 'cpu' or actions.dtype != torch.int32 or tuple(actions.shape) != (self._batch,):
-      raise ValueError('step_host takes a CPU int32 tensor of shape [batch]')
-    actions = actions.contiguous()
-    out = out or self.make_buffers()
-    houts = _lib.Outputs()
-    if host.observation is not None:
-      houts.observation = host.observation.data_ptr()
-    if host.reward is not None:
-      if host.reward.dtype == torch.float64:
-        houts.reward_f64 = host.reward.data_ptr()
-      else:
-        houts.reward = host.reward.data_ptr()
-    if host.discount is not None:
-      houts.discount = host.discount.data_ptr()
-    if host.step_type is not None:
-      houts.step_type = host.step_type.data_ptr()
-    dev_obs = None if self._ordinal < 0 else ctypes.c_void_p(out.observation.data_ptr())
+    if not (type(actions) is torch.Tensor and actions.dtype is torch.int32 and actions.device.type == 'cpu'
+            and actions.dim() == 1 and actions.shape[0] == self._batch and actions.is_contiguous()):
+      if not isinstance(actions, torch.Tensor):
+        actions = torch.as_tensor(np.asarray(actions))
+      if actions.device.type != 'cpu' or actions.dtype != torch.int32 or tuple(actions.shape) != (self._batch,):
+        raise ValueError('step_host takes a CPU int32 tensor of shape [batch]')
+      actions = actions.contiguous()
+    if out is None:
+      out = self.make_buffers()
+    houts = host.as_outputs()          # struct bsb_outputs over the host tensors, built once per StepBuffers
+    dev_obs = None if self._ordinal < 0 else out.observation.data_ptr()
     if self._ordinal < 0:        # host environment: one memory space; `out.observation` is the observation
+      houts = _lib.Outputs.from_buffer_copy(houts)
       houts.observation = out.observation.data_ptr()
-    _lib.check(self._lib.bsb_step_host(self._handle.ptr, ctypes.c_void_p(actions.data_ptr()), ctypes.byref(houts), dev_obs))
+    status = self._lib.bsb_step_host(self._handle.ptr, actions.data_ptr(), ctypes.byref(houts), dev_obs)
+    if status:
+      _lib.check(status)
     if self._ordinal < 0 and host.observation is not None:
       host.observation.copy_(out.observation)
-    return dm_env.TimeStep(step_type=host.step_type, reward=host.reward, discount=host.discount,
-                           observation=host.observation), out.observation
+    return host.timestep(), out.observation
 
   def rollout(self, num_steps: int, actions=None, action_seed: int = 0, out: Optional[StepBuffers] = None):
     """`num_steps` fused step() calls; actions [T,B] or None for on-device uniform random actions.
