@@ -89,6 +89,7 @@ int device_launch(bsb_env* e, LaunchArgs a, cudaStream_t stream) {
   a.work_counter = nullptr;
   a.work_base = 0;
   a.lazy_fetch = e->lazy_fetch;
+  a.l2_hint = e->l2_hint;
   int threads = e->block_threads;
   bool persistent = false;
   if (is_onehot && a.emit_bulk) {

@@ -43,6 +43,7 @@ struct bsb_env {
   int use_pdl;            // programmatic dependent launch between consecutive steps
   int zero_copy;          // bsb_step_host: kernel reads/writes pinned host buffers directly
   int lazy_fetch;         // persistent kernel: fetch the next chunk lazily (default) or one chunk ahead
+  int l2_hint;            // L2 eviction hint of the observation bulk stores (0 none, 1 evict_first, 2 evict_last)
   int num_sms;
   bsb::InfoNames names;
   std::vector<void*> allocs;

@@ -51,7 +51,7 @@ struct LaunchArgs {
   int32_t use_pdl;          // launched with programmatic stream serialization
   int32_t group_lanes;      // deep_sea bulk path: lanes per bulk store (power of two, 1..32)
   int32_t lazy_fetch;       // persistent launches: 1 = fetch the next chunk only when the current one is issued
-  int32_t reserved;
+  int32_t l2_hint;          // L2 policy of the observation bulk stores: 0 none, 1 evict_first (default), 2 evict_last
   unsigned long long* work_counter;  // persistent launches: monotonically increasing chunk counter (device)
   unsigned long long work_base;      // value of *work_counter at which this launch's chunk 0 starts
 };
@@ -141,6 +141,24 @@ __device__ __forceinline__ void st_stream(float* dst, float v) { __stcs(dst, v);
 __device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
   const uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
+}
+// Same store with an L2 eviction-priority hint (policy from createpolicy.fractional.L2::evict_first / evict_last).
+__device__ __forceinline__ void bulk_store_s2g_hint(void* gdst, const void* ssrc, uint32_t bytes, uint64_t policy) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst), "r"(s), "r"(bytes), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+// Bulk store with the launch's L2 policy: observations are written once and never re-read by this kernel, so they
+// are marked evict_first (default) -- measured 43.9 -> 40.8 us/step on the headline kernel (evict_last: 44.8).
+__device__ __forceinline__ void bulk_store_obs(void* gdst, const void* ssrc, uint32_t bytes, int l2_hint) {
+  if (l2_hint == 1) bulk_store_s2g_hint(gdst, ssrc, bytes, l2_policy_evict_first());
+  else if (l2_hint == 2) bulk_store_s2g_hint(gdst, ssrc, bytes, l2_policy_evict_last());
+  else bulk_store_s2g(gdst, ssrc, bytes);
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
@@ -445,7 +463,9 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
             fence_proxy_async_smem();
             __syncwarp();
             if (tid == 0) {
-              bulk_store_s2g(obs_t + (warp_base + g0) * (int64_t)K, group, (uint32_t)in_group * (uint32_t)K * 4u);
+              float* tile_dst = obs_t + (warp_base + g0) * (int64_t)K;
+              const uint32_t tile_bytes = (uint32_t)in_group * (uint32_t)K * 4u;
+              bulk_store_obs(tile_dst, group, tile_bytes, a.l2_hint);
               bulk_commit();
             }
             ++emitted;
@@ -469,7 +489,7 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
           if (buf) { poked_a1 = new_a; poked_b1 = new_b; } else { poked_a0 = new_a; poked_b0 = new_b; }
           fence_proxy_async_smem();
           __syncwarp();
-          if (tid == 0) { bulk_store_s2g(obs_t + warp_base * (int64_t)K, boards, (uint32_t)n_lanes * (uint32_t)K * 4u); bulk_commit(); }
+          if (tid == 0) { bulk_store_obs(obs_t + warp_base * (int64_t)K, boards, (uint32_t)n_lanes * (uint32_t)K * 4u, a.l2_hint); bulk_commit(); }
           ++emitted;
         } else {
           emit_twohot_vec(obs_t, warp_base, n_lanes, K, hot_a, hot_b, vec);
@@ -484,7 +504,7 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
         if (bulk) {
           fence_proxy_async_smem();
           __syncwarp();
-          if (tid == 0) { bulk_store_s2g(obs_t + warp_base * (int64_t)K, rows, (uint32_t)n_lanes * (uint32_t)K * 4u); bulk_commit(); }
+          if (tid == 0) { bulk_store_obs(obs_t + warp_base * (int64_t)K, rows, (uint32_t)n_lanes * (uint32_t)K * 4u, a.l2_hint); bulk_commit(); }
         } else {
           __syncwarp();
           flush_rows_vec(rows, obs_t, warp_base, n_lanes, K, vec);
