@@ -455,6 +455,7 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
             __syncwarp();
             if (s == 0) { if (tile_poked0 >= 0) { group[tile_poked0] = 0.f; tile_poked0 = -1; } }
             else        { if (tile_poked1 >= 0) { group[tile_poked1] = 0.f; tile_poked1 = -1; } }
+            __syncwarp();     // a thread of an earlier group may clear the very cell another thread sets now
             if (tid >= g0 && tid < g0 + in_group && hot >= 0) {
               const int cell = (tid - g0) * K + hot;
               group[cell] = 1.f;

@@ -1,0 +1,33 @@
+#!/usr/bin/env python
+"""A workload for compute-sanitizer that exercises the PERSISTENT deep_sea path (dynamic chunk counter, grouped
+TMA bulk stores with L2 hints, PDL) plus the catch / row bulk emitters at a size the sanitizer finishes quickly.
+
+    compute-sanitizer --tool memcheck  python tools/sanitize_check.py
+    compute-sanitizer --tool racecheck python tools/sanitize_check.py
+"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import bsuite_b200
+
+for bsuite_id, batch in (('deep_sea/11', 20000), ('deep_sea_stochastic/3', 40001), ('catch_noise/0', 5000), ('cartpole/0', 3000),
+                         ('umbrella_length/3', 2000), ('mnist/0', 1500)):
+  if bsuite_id.startswith('mnist'):
+    from bsuite_b200 import datasets
+    os.environ[datasets.ENV_VAR] = datasets.write_synthetic_mnist('/tmp/bsb_sanitize_mnist', 256, 16, 0)
+  results = []
+  for bulk in ('1', '0'):
+    os.environ['BSB_DEEP_SEA_BULK'] = bulk
+    os.environ['BSB_EMIT_BULK'] = bulk
+    env = bsuite_b200.load_from_id(bsuite_id, batch=batch, device='cuda', seed=3, track_episodes=True)
+    acts = torch.as_tensor(env.random_actions(4, action_seed=1, first_step=0)).cuda()
+    outs = [env.step(acts[i]).observation.clone() for i in range(4)]
+    ts = env.rollout(3, action_seed=2)
+    results.append(outs + [ts.observation.clone(), ts.reward.clone(), ts.step_type.clone()])
+    torch.cuda.synchronize()
+    env.close()
+  same = all(torch.equal(a, b) for a, b in zip(*results))
+  print(bsuite_id, batch, 'bulk == vector:', same, flush=True)
+  assert same
+print('sanitize workload finished')
