@@ -230,8 +230,12 @@ class BatchedEnvironment:
   def step(self, actions, out: Optional[StepBuffers] = None):
     """base.Environment.step for every lane (base.py:59-65); actions int [B]."""
     torch = self._torch
-    if not (type(actions) is torch.Tensor and actions.dtype is torch.int32 and actions.device == self._device
-            and actions.dim() == 1 and actions.shape[0] == self._batch and actions.is_contiguous()):
+    if not (type(actions) is torch.Tensor and actions.dtype is torch.int32 and actions.dim() == 1
+            and actions.shape[0] == self._batch and actions.is_contiguous()
+            and (actions.device == self._device
+                 # zero-copy: a PINNED host tensor is device-addressable at the same address (unified addressing),
+                 # the kernel reads it in place over PCIe; nothing is copied and nothing synchronises
+                 or (self._ordinal >= 0 and actions.device.type == 'cpu' and actions.is_pinned()))):
       actions = self._device_actions(actions, (self._batch,))
     if out is None:
       out = self.make_buffers()
@@ -239,6 +243,18 @@ class BatchedEnvironment:
     if status:
       _lib.check(status)
     return out.timestep()
+
+  def make_mixed_buffers(self) -> StepBuffers:
+    """Observation on the device, reward / discount / step_type in PINNED host memory: passed as `out=` to `step()`
+    the kernel writes the scalars straight into host memory (zero-copy), asynchronously -- synchronise the stream
+    (or an event) before reading them on the host."""
+    torch = self._torch
+    if self._ordinal < 0:
+      return self.make_buffers()
+    host = self.make_host_buffers()
+    return StepBuffers(observation=torch.empty((self._batch,) + tuple(self._spec.obs_shape), dtype=torch.float32,
+                                               device=self._device),
+                       reward=host.reward, discount=host.discount, step_type=host.step_type)
 
   def make_host_buffers(self, with_observation: bool = False) -> StepBuffers:
     """Pinned host tensors for `step_host` (reward / discount / step_type, optionally the observation).

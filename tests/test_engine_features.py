@@ -183,3 +183,22 @@ def test_step_host_matches_step(device, with_obs):
     np.testing.assert_array_equal(_np(dev_obs), _np(want.observation))
     if with_obs:
       np.testing.assert_array_equal(_np(got.observation), _np(want.observation))
+
+
+@pytest.mark.gpu
+def test_step_reads_pinned_host_actions_and_writes_pinned_host_scalars_in_place():
+  """Zero-copy through the ordinary step(): pinned host action tensor in, scalars into pinned host memory, the
+  observation on the device; identical to the all-device path."""
+  a = bsuite_b200.load_from_id('catch_noise/2', batch=4096, device='cuda', seed=6)
+  b = bsuite_b200.load_from_id('catch_noise/2', batch=4096, device='cuda', seed=6)
+  mixed = [b.make_mixed_buffers() for _ in range(2)]
+  assert mixed[0].reward.is_pinned() and mixed[0].observation.is_cuda
+  actions = torch.as_tensor(np.random.RandomState(0).randint(3, size=(30, 4096)).astype(np.int32)).pin_memory()
+  for t in range(30):
+    want = a.step(actions[t].cuda())
+    got = b.step(actions[t], out=mixed[t % 2])
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(got.reward.numpy(), want.reward.cpu().numpy())
+    np.testing.assert_array_equal(got.step_type.numpy(), want.step_type.cpu().numpy())
+    np.testing.assert_array_equal(got.discount.numpy(), want.discount.cpu().numpy())
+    assert torch.equal(got.observation, want.observation)
