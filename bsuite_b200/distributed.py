@@ -7,7 +7,7 @@ lane's trajectory does not depend on how the batch is sharded.  The only collect
 per-rank block of Logging statistics at log points (NCCL on GPUs; gloo in the CPU tests).
 """
 
-from typing import Any, Dict, Mapping, Optional, Tuple
+from typing import Any, Dict, Optional, Tuple
 
 from bsuite_b200 import registry
 

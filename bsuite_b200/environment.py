@@ -14,7 +14,7 @@ to allocate device memory and to pick the CUDA stream.
 """
 
 import ctypes
-from typing import Any, Dict, Optional, Sequence, Union
+from typing import Any, Dict, Optional
 
 import numpy as np
 

@@ -1,8 +1,6 @@
 """Recorder / CsvLogger: the Logging bookkeeping pinned by the reference's utils/wrappers_test.py:84-121, the log
 schedule of wrappers.py:140-147, and CSV files the reference's own csv_load can read."""
 
-import os
-
 import numpy as np
 import pytest
 
