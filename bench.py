@@ -229,6 +229,22 @@ def engine_main(args):
       cpu_baseline = {'value': None, 'unit': 'env-steps/s', 'cores': os.cpu_count(), 'kind': 'port',
                       'sample': 'failed: ' + (proc.stderr or '')[-300:]}
 
+  # For context only: the engine's own explicit host path (the same transition functions compiled for the CPU,
+  # one thread) on a 4 096-lane slice of the workload.
+  if cpu_baseline is not None and cpu_baseline.get('value'):
+    host_env = bsuite_b200.load_from_id(BSUITE_ID, batch=4096, device='cpu', seed=0)
+    host_buf = host_env.make_buffers()
+    host_act = torch.randint(0, 2, (8, 4096), dtype=torch.int32)
+    for t in range(3):
+      host_env.step(host_act[t], out=host_buf)
+    t0 = time.perf_counter()
+    n_host = 0
+    while time.perf_counter() - t0 < 1.5:
+      host_env.step(host_act[n_host % 8], out=host_buf)
+      n_host += 1
+    cpu_baseline['engine_host_path_1core'] = 4096 * n_host / (time.perf_counter() - t0)
+    host_env.close()
+
   B, K, W = BATCH_PER_GPU, args.steps, args.warmup
   lib = _lib.load()
   env = bsuite_b200.load_from_id(BSUITE_ID, batch=B, device=device, seed=0, lane_offset=rank * B,
