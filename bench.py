@@ -258,8 +258,8 @@ def engine_main(args):
     """Device-side reduction of the Logging accumulators + one all-gather of per-rank episode returns."""
     if args.no_track:
       return None
-    stats = env.episode_stats()
-    block = torch.stack([stats['total_return'].sum(), stats['episode'].sum(), stats['steps'].sum()])
+    sums = env.episode_stat_sums()          # one reduction kernel: (steps, episode, total_return, len, return)
+    block = sums[[2, 1, 0]]
     if world > 1:
       gathered = torch.empty(world * 3, dtype=block.dtype, device=device)
       dist.all_gather_into_tensor(gathered, block)

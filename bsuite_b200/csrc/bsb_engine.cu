@@ -185,6 +185,25 @@ __global__ void episode_stat_kernel(const EnvParams p, int field, int64_t calls,
   if (i < p.batch) dst[i] = episode_stat(p, i, field, calls);
 }
 
+__global__ void episode_sum_kernel(const EnvParams p, int64_t calls, double* dst5) {
+  __shared__ double partial[5][8];
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double v[5];
+#pragma unroll
+  for (int f = 0; f < 5; ++f) v[f] = i < p.batch ? episode_stat(p, i, f, calls) : 0.0;
+#pragma unroll
+  for (int f = 0; f < 5; ++f)
+    for (int o = 16; o > 0; o >>= 1) v[f] += __shfl_down_sync(0xffffffffu, v[f], o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) for (int f = 0; f < 5; ++f) partial[f][warp] = v[f];
+  __syncthreads();
+  if (threadIdx.x < 5) {
+    double s = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += partial[threadIdx.x][w];
+    atomicAdd(&dst5[threadIdx.x], s);
+  }
+}
+
 // ============================ extern "C" ====================================
 extern "C" {
 
@@ -421,6 +440,27 @@ int32_t bsb_read_episode_stats(bsb_env* env, int32_t field, double* dst, void* s
     BSB_CUDA(cudaGetLastError());
   } else {
     for (int64_t i = 0; i < B; ++i) dst[i] = episode_stat(env->p, i, field, env->steps_done);
+  }
+  return BSB_OK;
+}
+
+int32_t bsb_sum_episode_stats(bsb_env* env, double* dst5, void* stream) {
+  if (!env || !dst5) return fail(BSB_INVALID_ARGUMENT, "null argument");
+  if (!env->p.ep) return fail(BSB_INVALID_ARGUMENT, "environment was created without BSB_FLAG_TRACK_EPISODES");
+  const int64_t B = env->p.batch;
+  if (env->device >= 0) {
+    DeviceGuard guard(env->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    BSB_CUDA(cudaMemsetAsync(dst5, 0, 5 * sizeof(double), s));
+    episode_sum_kernel<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(env->p, env->steps_done, dst5);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    BSB_CUDA(cudaGetLastError());
+  } else {
+    for (int f = 0; f < 5; ++f) {
+      double s = 0.0;
+      for (int64_t i = 0; i < B; ++i) s += episode_stat(env->p, i, f, env->steps_done);
+      dst5[f] = s;
+    }
   }
   return BSB_OK;
 }

@@ -45,9 +45,8 @@ def gather_episode_returns(env, group=None) -> Dict[str, Any]:
   """
   import torch
   import torch.distributed as dist
-  stats = env.episode_stats()
-  block = torch.stack([stats['steps'].sum(), stats['episode'].sum(), stats['total_return'].sum(),
-                       torch.tensor(float(env.batch), dtype=torch.float64, device=stats['steps'].device)])
+  sums = env.episode_stat_sums()            # device-side reduction: (steps, episode, total_return, len, return)
+  block = torch.cat([sums[:3], torch.tensor([float(env.batch)], dtype=torch.float64, device=sums.device)])
   if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
     world = dist.get_world_size(group)
     gathered = torch.empty(world * block.numel(), dtype=block.dtype, device=block.device)

@@ -359,6 +359,15 @@ class BatchedEnvironment:
       result[name] = dst
     return result
 
+  def episode_stat_sums(self):
+    """Sums over this environment's lanes of (steps, episode, total_return, episode_len, episode_return): a float64
+    tensor [5] on the environment's device, produced by ONE reduction kernel (`bsb_sum_episode_stats`)."""
+    if not self._track:
+      raise RuntimeError('create the environment with track_episodes=True')
+    dst = self._torch.empty(5, dtype=self._torch.float64, device=self._device)
+    _lib.check(self._lib.bsb_sum_episode_stats(self._handle.ptr, dst.data_ptr(), self._stream()))
+    return dst
+
   # ---- checkpoint ------------------------------------------------------------
   def state_dict(self) -> Dict[str, Any]:
     n = ctypes.c_int64()

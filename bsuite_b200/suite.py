@@ -71,11 +71,8 @@ class SweepBatch:
   def local_returns(self):
     """float64 [n_ids, 3] on the device: per-id sums of (total_return, episode, steps) over this rank's lanes."""
     torch = self._torch
-    rows = []
-    for env in self.envs.values():
-      stats = env.episode_stats()
-      rows.append(torch.stack([stats['total_return'].sum(), stats['episode'].sum(), stats['steps'].sum()]))
-    return torch.stack(rows)
+    sums = torch.stack([env.episode_stat_sums() for env in self.envs.values()])   # one reduction kernel per id
+    return sums[:, [2, 1, 0]]
 
   def gather_returns(self):
     """The one collective of the path: all-gather of `local_returns()`; returns [world, n_ids, 3]."""

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define BSB_ABI_VERSION 3
+#define BSB_ABI_VERSION 4
 #define BSB_DEVICE_HOST (-1)
 #define BSB_MAX_INFO 4
 
@@ -233,6 +233,15 @@ int32_t bsb_read_info(bsb_env* env, int32_t index, double* dst, void* stream);
  */
 int32_t bsb_read_episode_stats(bsb_env* env, int32_t field, double* dst,
                                void* stream);
+
+/*
+ * Device-side reduction of the same five columns over the lanes of this
+ * environment: dst[5] (same memory space as the environment) receives the SUMS
+ * of steps, episode, total_return, episode_len, episode_return -- one small
+ * kernel, so a log point costs a 40-byte read (or a 40-byte all-gather across
+ * ranks) instead of five per-lane arrays.
+ */
+int32_t bsb_sum_episode_stats(bsb_env* env, double* dst5, void* stream);
 
 /* Flat snapshot of all lane state (checkpoint/resume; absent in the reference). */
 int32_t bsb_state_bytes(const bsb_env* env, int64_t* nbytes);

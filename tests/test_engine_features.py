@@ -202,3 +202,23 @@ def test_step_reads_pinned_host_actions_and_writes_pinned_host_scalars_in_place(
     np.testing.assert_array_equal(got.step_type.numpy(), want.step_type.cpu().numpy())
     np.testing.assert_array_equal(got.discount.numpy(), want.discount.cpu().numpy())
     assert torch.equal(got.observation, want.observation)
+
+
+@pytest.mark.parametrize('device', DEVICES)
+@pytest.mark.parametrize('batch', [1, 33, 1000])
+def test_episode_stat_sums_equal_the_per_lane_columns(device, batch):
+  """`bsb_sum_episode_stats` (one reduction kernel) against the per-lane columns of `bsb_read_episode_stats`:
+  the five sums are integers or sums of +-1 rewards here, so the comparison is exact."""
+  env = bsuite_b200.make('catch', batch=batch, device=device, seed=4,
+                         engine_kwargs=dict(track_episodes=True), rows=6, columns=4)
+  for T in (1, 40, 23):
+    env.rollout(T)
+    stats = env.episode_stats()
+    want = [float(stats[k].sum()) for k in ('steps', 'episode', 'total_return', 'episode_len', 'episode_return')]
+    assert _np(env.episode_stat_sums()).tolist() == want
+
+
+def test_episode_stat_sums_need_tracking():
+  env = bsuite_b200.make('catch', batch=4, device='cpu')
+  with pytest.raises(RuntimeError):
+    env.episode_stat_sums()

@@ -61,6 +61,7 @@ def main():
   ap.add_argument('--only', default=None)
   ap.add_argument('--steps', type=int, default=60)
   ap.add_argument('--rollout', type=int, default=16)
+  ap.add_argument('--batch', type=int, default=0, help='override every configuration\'s batch size')
   args = ap.parse_args()
   mnist_dir = '/tmp/bsb_bench_mnist'
   datasets.write_synthetic_mnist(mnist_dir, 4096, 16, 0)
@@ -69,6 +70,8 @@ def main():
   for name, (kind, what, kw), batch, state_bytes in CONFIGS:
     if args.only and args.only not in name:
       continue
+    if args.batch:
+      batch = args.batch
     env = bsuite_b200.load_from_id(what, batch=batch, device='cuda', seed=0)
     numel = 1
     for d in env.obs_shape:
