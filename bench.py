@@ -388,6 +388,42 @@ def engine_main(args):
              'note': 'bsb_rollout: 16 steps per launch, lane state in registers, actions sampled on device'}
     del fbuf
 
+  # ---- the same single-step launches replayed from a CUDA graph ("graph-captured") ------------
+  graph_replay = None
+  if not args.skip_graph:
+    reps, g_ms, g_err = max(1, K // RING), 0.0, None
+    try:     # an optional leg must not take the line down (and holds no collective, so no rank can strand another)
+      genv = bsuite_b200.load_from_id(BSUITE_ID, batch=B, device=device, seed=0, lane_offset=rank * B,
+                                      track_episodes=not args.no_track)
+      graphed = genv.capture(RING)          # RING launches per graph, each writing its own buffer set (> L2 in total)
+      graphed.actions.copy_(actions[:RING])
+      for _ in range(3):
+        graphed.replay()
+      torch.cuda.synchronize()
+      g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      g0.record()
+      for _ in range(reps):
+        graphed.replay()
+      g1.record()
+      torch.cuda.synchronize()
+      g_ms = g0.elapsed_time(g1)
+      del graphed
+      genv.close()
+    except Exception as exc:  # pylint: disable=broad-except
+      g_err = repr(exc)[:300]
+    gms = torch.tensor([g_ms, 0.0 if g_err is None else 1.0], dtype=torch.float64, device=device)
+    if world > 1:
+      dist.all_reduce(gms, op=dist.ReduceOp.MAX)
+    if float(gms[1]) > 0:
+      graph_replay = {'value': None, 'error': g_err or 'failed on another rank'}
+    else:
+      per_step_s = float(gms[0]) * 1e-3 / (reps * RING)
+      graph_replay = {'value': world * B / per_step_s, 'unit': 'env-steps/s', 'us_per_step': per_step_s * 1e6,
+                      'steps_per_graph': RING, 'replays': reps,
+                      'note': 'cudaGraphLaunch of RING captured single-step launches; step counter and chunk scheduler '
+                              'live in device memory (graph-safe mode); programmatic edges between the captured '
+                              'launches; ranks are not barrier-aligned for this leg'}
+
   if rank == 0:
     peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(peaks_path):
@@ -425,6 +461,7 @@ def engine_main(args):
                         'pinned scalar outputs, launches queued, one synchronise at the end.'},
         'gpu_launches': int(launches),
         'fused_rollout': fused,
+        'graph_replay': graph_replay,
         'clocks': clocks,
         'log_point': None if summary is None else [float(x) for x in summary.cpu()[:3]],
     }
@@ -444,6 +481,7 @@ def main():
   parser.add_argument('--skip-host-obs', action='store_true')
   parser.add_argument('--no-track', action='store_true', help='disable the per-lane Logging accumulators')
   parser.add_argument('--skip-fused', action='store_true', help='skip the T-fused rollout variant')
+  parser.add_argument('--skip-graph', action='store_true', help='skip the CUDA-graph replay variant')
   args = parser.parse_args()
   if args.warmup < 3:
     args.warmup = 3

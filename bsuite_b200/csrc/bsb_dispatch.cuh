@@ -105,7 +105,7 @@ int device_launch(bsb_env* e, LaunchArgs a, cudaStream_t stream) {
       a.group_lanes = m; threads = 32; persistent = e->deep_sea_persistent != 0;
     }
   }
-  a.use_pdl = (e->use_pdl && a.mode == MODE_STEP && a.T == 1) ? 1 : 0;
+  a.use_pdl = (e->use_pdl && !a.no_pdl && a.mode == MODE_STEP && a.T == 1) ? 1 : 0;
   const size_t per_warp = smem_floats_per_warp<F>(K, a.emit_bulk != 0, a.group_lanes) * sizeof(float);
   size_t smem = per_warp * (size_t)(threads / 32);
   while (smem > 96 * 1024 && threads > 32) { threads >>= 1; smem = per_warp * (size_t)(threads / 32); }
@@ -120,8 +120,8 @@ int device_launch(bsb_env* e, LaunchArgs a, cudaStream_t stream) {
     const int64_t resident = (int64_t)e->num_sms * (per_sm < 1 ? 1 : (per_sm > 16 ? 16 : per_sm));
     if (grid > resident) {
       grid = resident;
-      a.work_counter = e->work_counter;
-      a.work_base = e->work_base;
+      a.work_counter = a.clock ? a.clock + 1 : e->work_counter;
+      a.work_base = a.clock ? 0ull : e->work_base;
     } else {
       persistent = false;      // everything is resident anyway: one chunk per warp
     }
@@ -141,7 +141,8 @@ int device_launch(bsb_env* e, LaunchArgs a, cudaStream_t stream) {
   }
   BSB_CUDA(cudaLaunchKernelEx(&cfg, kernel, e->p, a));
   // chunks [warps, n_chunks) are fetched once each and every warp makes exactly one failing fetch
-  if (a.work_counter) e->work_base += (unsigned long long)((B + 31) / 32);
+  // (graph-safe mode: the last CTA zeroes the counter instead)
+  if (a.work_counter && !a.clock) e->work_base += (unsigned long long)((B + 31) / 32);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return BSB_OK;
 }

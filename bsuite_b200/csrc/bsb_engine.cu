@@ -77,8 +77,15 @@ template <class T> int env_alloc_t(bsb_env* e, T** out, size_t count, bool snaps
   return rc;
 }
 
-int run(bsb_env* e, const LaunchArgs& a, cudaStream_t stream) {
+int run(bsb_env* e, const LaunchArgs& args, cudaStream_t stream) {
   DeviceGuard guard(e->device);
+  LaunchArgs a = args;
+  if (e->device >= 0) {
+    cudaStreamCaptureStatus capture = cudaStreamCaptureStatusNone;
+    BSB_CUDA(cudaStreamIsCapturing(stream, &capture));
+    if (capture != cudaStreamCaptureStatusNone) { e->graph_safe = true; a.no_pdl = e->graph_pdl ? 0 : 1; }
+    if (e->graph_safe) a.clock = e->clock;      // a.step0 == e->steps_done, which no longer moves
+  }
   switch (e->p.family) {
     case BSB_DEEP_SEA: return run_deep_sea(e, a, stream);
     case BSB_CATCH: return run_catch(e, a, stream);
@@ -180,17 +187,26 @@ void destroy_env(bsb_env* e) {
 
 }  // namespace
 
-__global__ void episode_stat_kernel(const EnvParams p, int field, int64_t calls, double* dst) {
+__global__ void episode_stat_kernel(const EnvParams p, int field, int64_t calls, const unsigned long long* clock, double* dst) {
+  if (clock) calls += (int64_t)*clock;      // graph-safe mode: steps since the switch are counted on the device
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < p.batch) dst[i] = episode_stat(p, i, field, calls);
 }
 
-__global__ void episode_sum_kernel(const EnvParams p, int64_t calls, double* dst5) {
-  __shared__ double partial[5][8];
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  double v[5];
+// Sums of the five Logging columns over the lanes.  Deterministic: a fixed grid (a function of the batch only) of
+// block-strided partial sums lands in scratch[block][5]; the block that finishes last adds the partials in block
+// order and re-arms the ticket.  (No floating-point atomics: the result must not depend on scheduling -- a graph
+// replay and an eager call must agree to the bit.)
+constexpr int kSumBlocks = 64, kSumThreads = 256;
+__global__ void episode_sum_kernel(const EnvParams p, int64_t calls, const unsigned long long* clock,
+                                   double* scratch, unsigned long long* ticket, double* dst5) {
+  if (clock) calls += (int64_t)*clock;
+  __shared__ double partial[5][kSumThreads / 32];
+  __shared__ bool is_last;
+  double v[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.batch; i += (int64_t)gridDim.x * blockDim.x)
 #pragma unroll
-  for (int f = 0; f < 5; ++f) v[f] = i < p.batch ? episode_stat(p, i, f, calls) : 0.0;
+    for (int f = 0; f < 5; ++f) v[f] += episode_stat(p, i, f, calls);
 #pragma unroll
   for (int f = 0; f < 5; ++f)
     for (int o = 16; o > 0; o >>= 1) v[f] += __shfl_down_sync(0xffffffffu, v[f], o);
@@ -200,8 +216,20 @@ __global__ void episode_sum_kernel(const EnvParams p, int64_t calls, double* dst
   if (threadIdx.x < 5) {
     double s = 0.0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += partial[threadIdx.x][w];
-    atomicAdd(&dst5[threadIdx.x], s);
+    scratch[blockIdx.x * 5 + threadIdx.x] = s;
+    __threadfence();
   }
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(ticket, 1ull) == (unsigned long long)gridDim.x - 1ull;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (threadIdx.x < 5) {
+    double s = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(scratch + b * 5 + threadIdx.x);
+    dst5[threadIdx.x] = s;
+  }
+  if (threadIdx.x == 0) *ticket = 0ull;
 }
 
 // ============================ extern "C" ====================================
@@ -231,7 +259,7 @@ int32_t bsb_create(const bsb_config* config, int64_t batch, int32_t device, uint
 
   bsb_env* e = new bsb_env();
   memset(&e->p, 0, sizeof(e->p));
-  e->device = device; e->steps_done = 0; e->names = info_names(c.family);
+  e->device = device; e->steps_done = 0; e->graph_safe = false; e->clock = nullptr; e->sum_scratch = nullptr; e->names = info_names(c.family);
   {  // tuning knobs (environment variables, read once per handle)
     auto flag = [](const char* name, int dflt) { const char* v = getenv(name); return v ? (atoi(v) != 0 ? 1 : 0) : dflt; };
     const char* bt = getenv("BSB_BLOCK_THREADS");
@@ -242,6 +270,7 @@ int32_t bsb_create(const bsb_config* config, int64_t batch, int32_t device, uint
     { const char* g = getenv("BSB_DEEP_SEA_GROUP"); e->deep_sea_group = g ? atoi(g) : 0;
       if (e->deep_sea_group < 0 || e->deep_sea_group > 32 || (e->deep_sea_group & (e->deep_sea_group - 1))) e->deep_sea_group = 0; }
     e->use_pdl = flag("BSB_PDL", 1);
+    e->graph_pdl = flag("BSB_GRAPH_PDL", 1);
     e->deep_sea_persistent = flag("BSB_DEEP_SEA_PERSISTENT", 1);
     e->zero_copy = flag("BSB_ZERO_COPY", 1);
     e->lazy_fetch = flag("BSB_LAZY_FETCH", 1);
@@ -297,7 +326,7 @@ int32_t bsb_create(const bsb_config* config, int64_t batch, int32_t device, uint
     BSB_TRY(env_upload(e, l, c.table2, (size_t)c.table2_bytes));
     p.images = d; p.labels = l;
   }
-  if (device >= 0) BSB_TRY(env_alloc_t(e, &e->work_counter, 1, false));
+  if (device >= 0) { BSB_TRY(env_alloc_t(e, &e->work_counter, 1, false)); BSB_TRY(env_alloc_t(e, &e->clock, 4, false)); BSB_TRY(env_alloc_t(e, &e->sum_scratch, kSumBlocks * 5 + 1, false)); }
   // lane state
   BSB_TRY(env_alloc_t(e, &p.st_word, B, true));
   if (c.family == BSB_MEMORY_CHAIN) BSB_TRY(env_alloc_t(e, &p.st_ctx, B, true));
@@ -361,16 +390,31 @@ int32_t bsb_batch(const bsb_env* env, int64_t* batch) {
   if (!env || !batch) return fail(BSB_INVALID_ARGUMENT, "null argument");
   *batch = env->p.batch; return BSB_OK;
 }
+// Host view of the step counter.  In graph-safe mode the count lives on the device (graph replays advance it
+// without the host seeing them): wait for the device and read it back.
+static int current_steps(const bsb_env* env, int64_t* steps) {
+  *steps = env->steps_done;
+  if (env->graph_safe) {
+    DeviceGuard guard(env->device);
+    unsigned long long since = 0;
+    BSB_CUDA(cudaDeviceSynchronize());
+    BSB_CUDA(cudaMemcpy(&since, env->clock, sizeof(since), cudaMemcpyDeviceToHost));
+    *steps += (int64_t)since;
+  }
+  return BSB_OK;
+}
+static void advance_steps(bsb_env* env, int64_t n) { if (!env->graph_safe) env->steps_done += n; }
+
 int32_t bsb_steps_done(const bsb_env* env, int64_t* steps) {
   if (!env || !steps) return fail(BSB_INVALID_ARGUMENT, "null argument");
-  *steps = env->steps_done; return BSB_OK;
+  return current_steps(env, steps);
 }
 
 int32_t bsb_reset(bsb_env* env, const bsb_outputs* out, void* stream) {
   if (!env || !out || !out->observation) return fail(BSB_INVALID_ARGUMENT, "bsb_reset needs outputs with an observation buffer");
   LaunchArgs a = make_args(env, out, nullptr, 1, MODE_RESET);
   int rc = run(env, a, static_cast<cudaStream_t>(stream));
-  if (rc == BSB_OK) env->steps_done += 1;
+  if (rc == BSB_OK) advance_steps(env, 1);
   return rc;
 }
 
@@ -378,7 +422,7 @@ int32_t bsb_step(bsb_env* env, const int32_t* actions, const bsb_outputs* out, v
   if (!env || !actions || !out || !out->observation) return fail(BSB_INVALID_ARGUMENT, "bsb_step needs actions and outputs with an observation buffer");
   LaunchArgs a = make_args(env, out, actions, 1, MODE_STEP);
   int rc = run(env, a, static_cast<cudaStream_t>(stream));
-  if (rc == BSB_OK) env->steps_done += 1;
+  if (rc == BSB_OK) advance_steps(env, 1);
   return rc;
 }
 
@@ -389,7 +433,7 @@ int32_t bsb_rollout(bsb_env* env, int64_t num_steps, const int32_t* actions, uin
   LaunchArgs a = make_args(env, out, actions, num_steps, MODE_STEP);
   a.action_seed = action_seed; a.actions_out = actions_out;
   int rc = run(env, a, static_cast<cudaStream_t>(stream));
-  if (rc == BSB_OK) env->steps_done += num_steps;
+  if (rc == BSB_OK) advance_steps(env, num_steps);
   return rc;
 }
 
@@ -435,7 +479,7 @@ int32_t bsb_read_episode_stats(bsb_env* env, int32_t field, double* dst, void* s
   const int64_t B = env->p.batch;
   if (env->device >= 0) {
     DeviceGuard guard(env->device);
-    episode_stat_kernel<<<(unsigned)((B + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(env->p, field, env->steps_done, dst);
+    episode_stat_kernel<<<(unsigned)((B + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(env->p, field, env->steps_done, env->graph_safe ? env->clock : nullptr, dst);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     BSB_CUDA(cudaGetLastError());
   } else {
@@ -450,9 +494,11 @@ int32_t bsb_sum_episode_stats(bsb_env* env, double* dst5, void* stream) {
   const int64_t B = env->p.batch;
   if (env->device >= 0) {
     DeviceGuard guard(env->device);
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    BSB_CUDA(cudaMemsetAsync(dst5, 0, 5 * sizeof(double), s));
-    episode_sum_kernel<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(env->p, env->steps_done, dst5);
+    int64_t blocks = (B + kSumThreads - 1) / kSumThreads;
+    if (blocks > kSumBlocks) blocks = kSumBlocks;
+    episode_sum_kernel<<<(unsigned)blocks, kSumThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        env->p, env->steps_done, env->graph_safe ? env->clock : nullptr, env->sum_scratch,
+        reinterpret_cast<unsigned long long*>(env->sum_scratch + kSumBlocks * 5), dst5);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     BSB_CUDA(cudaGetLastError());
   } else {
@@ -479,8 +525,10 @@ int32_t bsb_get_state(bsb_env* env, void* dst_host, int64_t nbytes, void* stream
   if (nbytes != need) return fail(BSB_INVALID_ARGUMENT, "state buffer has the wrong size");
   DeviceGuard guard(env->device);
   char* dst = static_cast<char*>(dst_host);
-  memcpy(dst, &env->steps_done, sizeof(int64_t)); dst += sizeof(int64_t);
   if (env->device >= 0) BSB_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  int64_t steps = 0;
+  { int rc = current_steps(env, &steps); if (rc != BSB_OK) return rc; }
+  memcpy(dst, &steps, sizeof(int64_t)); dst += sizeof(int64_t);
   for (size_t k = 0; k < env->state_blocks.size(); ++k) {
     if (env->device >= 0) BSB_CUDA(cudaMemcpy(dst, env->state_blocks[k].first, env->state_blocks[k].second, cudaMemcpyDeviceToHost));
     else memcpy(dst, env->state_blocks[k].first, env->state_blocks[k].second);
@@ -496,8 +544,18 @@ int32_t bsb_set_state(bsb_env* env, const void* src_host, int64_t nbytes, void* 
   if (nbytes != need) return fail(BSB_INVALID_ARGUMENT, "state buffer has the wrong size");
   DeviceGuard guard(env->device);
   const char* src = static_cast<const char*>(src_host);
-  memcpy(&env->steps_done, src, sizeof(int64_t)); src += sizeof(int64_t);
   if (env->device >= 0) BSB_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  int64_t restored = 0;
+  memcpy(&restored, src, sizeof(int64_t)); src += sizeof(int64_t);
+  if (env->graph_safe) {
+    // steps_done is baked into the captured launches as their base: it must not move.  The restored count goes
+    // into the device clock as an offset from that base (two's complement, so it may be "negative").
+    const unsigned long long since = (unsigned long long)restored - (unsigned long long)env->steps_done;
+    BSB_CUDA(cudaDeviceSynchronize());
+    BSB_CUDA(cudaMemcpy(env->clock, &since, sizeof(since), cudaMemcpyHostToDevice));
+  } else {
+    env->steps_done = restored;
+  }
   for (size_t k = 0; k < env->state_blocks.size(); ++k) {
     if (env->device >= 0) BSB_CUDA(cudaMemcpy(env->state_blocks[k].first, src, env->state_blocks[k].second, cudaMemcpyHostToDevice));
     else memcpy(env->state_blocks[k].first, src, env->state_blocks[k].second);

@@ -31,7 +31,12 @@ extern std::atomic<int64_t> g_launches;                // kernels launched by th
 struct bsb_env {
   bsb::EnvParams p;
   int device;             // BSB_DEVICE_HOST or CUDA ordinal
-  int64_t steps_done;
+  int64_t steps_done;     // step() calls so far (host counter; frozen at the switch to graph-safe mode)
+  // Graph-safe mode: entered for good when a launch of this handle is first captured into a CUDA graph.  From
+  // then on the device clock counts the steps (kernel comment in bsb_kernels.cuh) and steps = steps_done + clock[0].
+  bool graph_safe;
+  unsigned long long* clock;         // device: {steps since the switch, chunk counter, finished CTAs}
+  double* sum_scratch;               // device: bsb_sum_episode_stats partials [64][5] + the ticket
   // tuning knobs (environment variables, read once per handle)
   int block_threads;      // CTA size of the transition kernel (32 / 64 / 128)
   int emit_bulk;          // TMA bulk stores for the row / board emitters
@@ -41,6 +46,7 @@ struct bsb_env {
   unsigned long long* work_counter;  // device counter of the dynamic chunk scheduler
   unsigned long long work_base;      // its value when the next launch starts
   int use_pdl;            // programmatic dependent launch between consecutive steps
+  int graph_pdl;          // ... also between launches captured into a CUDA graph (programmatic graph edges)
   int zero_copy;          // bsb_step_host: kernel reads/writes pinned host buffers directly
   int lazy_fetch;         // persistent kernel: fetch the next chunk lazily (default) or one chunk ahead
   int l2_hint;            // L2 eviction hint of the observation bulk stores (0 none, 1 evict_first, 2 evict_last)

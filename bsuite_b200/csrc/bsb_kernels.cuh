@@ -54,6 +54,10 @@ struct LaunchArgs {
   int32_t l2_hint;          // L2 policy of the observation bulk stores: 0 none, 1 evict_first (default), 2 evict_last
   unsigned long long* work_counter;  // persistent launches: monotonically increasing chunk counter (device)
   unsigned long long work_base;      // value of *work_counter at which this launch's chunk 0 starts
+  // Device clock (graph-safe mode, see the kernel): {steps advanced in this mode, chunk counter, finished CTAs}.
+  // Null in the default mode, where `step0` / `work_base` arrive as launch arguments from the host's counters.
+  unsigned long long* clock;
+  int32_t no_pdl;           // set while the stream is being captured
 };
 
 enum { MODE_STEP = 0, MODE_RESET = 1, MODE_INIT = 2 };
@@ -320,6 +324,12 @@ template <> struct Descriptor<Mnist> {
 //     first chunk is its own index (no atomic on the start-up path); the counter deals the rest and is never
 //     reset: a launch with C chunks and W warps performs exactly C atomicAdds (C - W successful fetches plus one
 //     failing fetch per warp), so launch k starts at work_base_k = work_base_(k-1) + C.
+// Graph-safe mode (a.clock != null; the handle switches to it for good the first time one of its launches is
+// captured into a CUDA graph): launch arguments are frozen in a graph, so everything that changes from launch to
+// launch lives in device memory instead.  clock[0] = steps this handle has advanced since the switch (step index
+// = a.step0 + clock[0]: the on-device action stream and the Logging columns depend on it), clock[1] = chunk
+// counter, clock[2] = CTAs that have finished.  The CTA that finishes last advances clock[0] by T and zeroes the
+// other two; every CTA reads clock[0] before it counts itself finished, so the update cannot overtake a reader.
 // Register budget per family (second __launch_bounds__ argument, counted in 128-thread blocks per SM).  The
 // generic kernel is register-hungry (two Philox streams, action stream, accumulators); left alone ptxas takes
 // 160-220 registers and 64-thread CTAs then run at 8 warps/SM, which starves the latency-bound small families.
@@ -361,6 +371,8 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
   // Wait for the previous step's kernel (it wrote the lane state read below), THEN allow the next step's kernel
   // to become resident: its CTAs park at their own wait, so at most one dependent grid is ever pending.
   if (a.use_pdl) { pdl_wait(); pdl_launch_dependents(); }
+  int64_t step0 = a.step0;
+  if (a.clock) step0 += (int64_t)*reinterpret_cast<volatile unsigned long long*>(a.clock);
 
   const int64_t n_chunks = (B + 31) / 32;
   const bool dynamic = a.work_counter != nullptr;
@@ -370,7 +382,7 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
   const int64_t total_warps = (int64_t)gridDim.x * warps_per_cta;
   auto fetch_chunk = [&]() -> int64_t {
     unsigned long long v = 0;
-    if (tid == 0) v = atomicAdd(a.work_counter, 1ull) - a.work_base;
+    if (tid == 0) v = atomicAdd(a.work_counter, 1ull) - a.work_base;      // graph-safe mode: clock + 1, base 0
     return total_warps + (int64_t)__shfl_sync(0xffffffffu, v, 0);
   };
   int64_t cur_chunk = (int64_t)blockIdx.x * warps_per_cta + warp;
@@ -428,11 +440,11 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
         int32_t action = 0;
         if (a.mode == MODE_STEP) {
           action = a.actions ? a.actions[off]
-                             : action_stream.sample(a.action_seed, p.lane_offset + (uint64_t)lane, (uint64_t)(a.step0 + t), p.num_actions);
+                             : action_stream.sample(a.action_seed, p.lane_offset + (uint64_t)lane, (uint64_t)(step0 + t), p.num_actions);
           if (a.actions_out) a.actions_out[off] = action;
         }
         const StepOut o = lane_transition<F, R, R>(p, lane, L, rng, wrng, action, a.mode, kNoise);
-        if (kTrack) ep.track(p, lane, o, a.step0 + t);
+        if (kTrack) ep.track(p, lane, o, step0 + t);
         if (a.reward) a.reward[off] = (float)o.reward;
         if (a.reward_f64) a.reward_f64[off] = o.reward;
         if (a.discount) a.discount[off] = o.discount;
@@ -523,6 +535,18 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
     if (dynamic && lazy) cur_chunk = fetch_chunk();        // lazy: nothing was reserved while working
   }
   if (any_bulk && tid == 0) bulk_wait_read<0>();      // shared memory must outlive the last bulk read
+  if (a.clock) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(a.clock + 2, 1ull) == (unsigned long long)gridDim.x - 1ull) {
+        a.clock[0] = (unsigned long long)(step0 - a.step0) + (a.mode == MODE_INIT ? 0ull : (unsigned long long)a.T);
+        a.clock[1] = 0ull;
+        a.clock[2] = 0ull;
+        __threadfence();
+      }
+    }
+  }
 }
 
 #endif  // __CUDACC__

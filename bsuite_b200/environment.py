@@ -139,6 +139,25 @@ class StepBuffers:
     return self._timestep
 
 
+class GraphedSteps:
+  """`num_steps` step() calls of one environment recorded in a CUDA graph (`BatchedEnvironment.capture`).
+
+  Write the next actions into `actions` ([T, B] int32, absent when the actions are sampled on the device), call
+  `replay()`, read `timestep` (fields with a leading T axis, the same tensors every time).  The environment keeps
+  its step count on the device from the first capture on, so eager calls and replays can be mixed freely."""
+
+  def __init__(self, env, graph, actions, buffers):
+    self.env = env
+    self.graph = graph
+    self.actions = actions
+    self.buffers = buffers
+    self.timestep = buffers.timestep()
+
+  def replay(self):
+    self.graph.replay()
+    return self.timestep
+
+
 class BatchedEnvironment:
   """`batch` independent lanes of one environment on one device."""
 
@@ -319,6 +338,39 @@ class BatchedEnvironment:
     _lib.check(self._lib.bsb_rollout(self._handle.ptr, num_steps, act_ptr, int(action_seed) & _MASK64,
                                      ctypes.byref(outputs), act_out, self._stream()))
     return out.timestep()
+
+  def capture(self, num_steps: int = 1, sample_actions: bool = False, fused: bool = False,
+              action_seed: int = 0) -> GraphedSteps:
+    """Records `num_steps` steps into a CUDA graph: one launch per step (`fused=False`, the reference's call
+    pattern, baselines/experiment.py:45-57) or one fused rollout launch.  Launch arguments are frozen in a graph,
+    so the library moves this handle's step counter and chunk scheduler to device memory when it sees the capture
+    (include/bsuite_b200.h, "CUDA graphs").  One eager pass is made first on a snapshot of the lane state (module
+    loading and function attributes must not happen inside a capture); the state is restored before recording."""
+    torch = self._torch
+    if self._ordinal < 0:
+      raise RuntimeError('CUDA graphs need a CUDA environment')
+    T = int(num_steps)
+    buffers = self.make_buffers(T, with_actions=sample_actions)
+    actions = None if sample_actions else torch.zeros((T, self._batch), dtype=torch.int32, device=self._device)
+    slices = [StepBuffers(buffers.observation[t:t + 1], buffers.reward[t:t + 1], buffers.discount[t:t + 1],
+                          buffers.step_type[t:t + 1], None if buffers.actions is None else buffers.actions[t:t + 1])
+              for t in range(T)]
+
+    def record():
+      if fused:
+        self.rollout(T, actions=actions, action_seed=action_seed, out=buffers)
+      else:
+        for t in range(T):
+          self.rollout(1, actions=None if actions is None else actions[t:t + 1], action_seed=action_seed, out=slices[t])
+
+    state = self.state_dict()
+    record()
+    torch.cuda.synchronize(self._device)
+    self.load_state_dict(state)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+      record()
+    return GraphedSteps(self, graph, actions, buffers)
 
   def random_actions(self, num_steps: int, action_seed: int = 0, first_step: Optional[int] = None) -> np.ndarray:
     """Host mirror of the on-device action sampler for this environment's lanes."""

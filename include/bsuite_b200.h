@@ -235,6 +235,16 @@ int32_t bsb_read_episode_stats(bsb_env* env, int32_t field, double* dst,
                                void* stream);
 
 /*
+ * CUDA graphs.  bsb_step / bsb_reset / bsb_rollout / bsb_read_* / bsb_sum_episode_stats may be called on a stream
+ * that is being captured.  A graph freezes launch arguments, so the first captured launch moves the handle's step
+ * counter (it indexes the on-device action stream and the Logging columns) and its chunk scheduler into device
+ * memory, for good: replays and eager calls can then be mixed in any order, and bsb_steps_done / bsb_get_state
+ * synchronise the device to read the counter back.  Consecutive captured steps keep their programmatic dependent
+ * launch (it becomes a programmatic graph edge; BSB_GRAPH_PDL=0 turns that off).
+ * bsb_step_host (internal streams and a host synchronise) cannot be captured.
+ */
+
+/*
  * Device-side reduction of the same five columns over the lanes of this
  * environment: dst[5] (same memory space as the environment) receives the SUMS
  * of steps, episode, total_return, episode_len, episode_return -- one small

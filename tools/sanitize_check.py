@@ -30,4 +30,18 @@ for bsuite_id, batch in (('deep_sea/11', 20000), ('deep_sea_stochastic/3', 40001
   same = all(torch.equal(a, b) for a, b in zip(*results))
   print(bsuite_id, batch, 'bulk == vector:', same, flush=True)
   assert same
+# Graph-safe mode: device clock, chunk counter re-armed by the last CTA, the deterministic two-stage reduction.
+for bsuite_id, batch in (('deep_sea/11', 20000), ('catch/0', 5000)):
+  env = bsuite_b200.load_from_id(bsuite_id, batch=batch, device='cuda', seed=3, track_episodes=True)
+  twin = bsuite_b200.load_from_id(bsuite_id, batch=batch, device='cuda', seed=3, track_episodes=True)
+  graphed = env.capture(2, sample_actions=True, action_seed=5)
+  for _ in range(3):
+    got = graphed.replay()
+    want = twin.rollout(2, action_seed=5)
+    assert torch.equal(got.observation, want.observation) and torch.equal(got.reward, want.reward)
+  env.step(torch.zeros(batch, dtype=torch.int32, device='cuda'))
+  twin.step(torch.zeros(batch, dtype=torch.int32, device='cuda'))
+  assert torch.equal(env.episode_stat_sums(), twin.episode_stat_sums()) and env.steps_done == twin.steps_done == 7
+  print(bsuite_id, batch, 'graph replay == eager: True', flush=True)
+  env.close(); twin.close()
 print('sanitize workload finished')
