@@ -268,6 +268,10 @@ int32_t bsb_set_state(bsb_env* env, const void* src_host, int64_t nbytes,
  * When `actions` and the requested scalar outputs are PINNED host memory the
  * kernel accesses them in place over PCIe (zero-copy: no separate H2D / D2H
  * copies); pageable buffers take the staged-copy path.
+ * Stream order: the work runs on a stream the handle owns and is complete on
+ * return, so later calls on any stream see its results; work enqueued EARLIER
+ * on this handle through bsb_step / bsb_rollout on a caller's stream is not
+ * waited for -- synchronise that stream first if there is any in flight.
  */
 int32_t bsb_step_host(bsb_env* env, const int32_t* actions,
                       const bsb_outputs* host_out, float* device_obs);
