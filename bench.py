@@ -390,7 +390,7 @@ def engine_main(args):
 
   # ---- the same single-step launches replayed from a CUDA graph ("graph-captured") ------------
   graph_replay = None
-  if not args.skip_graph:
+  if not args.skip_graph and world == 1:      # a per-GPU figure; the multi-rank runs measure scaling, not this
     reps, g_ms, g_err = max(1, K // RING), 0.0, None
     try:     # an optional leg must not take the line down (and holds no collective, so no rank can strand another)
       genv = bsuite_b200.load_from_id(BSUITE_ID, batch=B, device=device, seed=0, lane_offset=rank * B,
