@@ -3,7 +3,7 @@
  *
  * This header is the drop-in boundary for the one hot path this repo builds:
  * the per-environment step()/reset() dynamics of google-deepmind/bsuite
- * (reference: bsuite/environments/*.py, experiments/cartpole_swingup,
+ * (reference: bsuite/environments/<name>.py, experiments/cartpole_swingup,
  * utils/wrappers.py::RewardNoise/RewardScale), executed for B independent
  * environment "lanes" in lock-step.
  *
