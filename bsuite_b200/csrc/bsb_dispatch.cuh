@@ -90,6 +90,16 @@ int device_launch(bsb_env* e, LaunchArgs a, cudaStream_t stream) {
   a.work_base = 0;
   a.lazy_fetch = e->lazy_fetch;
   a.l2_hint = e->l2_hint;
+  // Lanes per chunk.  The image emitter walks the chunk's lanes one 3 KB tile at a time, so it is bound by how many
+  // warps share the batch: keep >= 4 warps per SM by halving the chunk (down to 8 lanes) when 32-lane chunks would
+  // not.  Measured at 4 096 lanes (rollout us/step, 32-lane vs 8-lane chunks): mnist 14.8 -> 4.2; the deep_sea bulk
+  // path gets WORSE (N = 32: 2.4 -> 3.5, N = 50: 5.6 -> 6.0 -- fewer, larger TMA stores win), so it keeps 32.
+  int chunk = 32;
+  if (EmitKind<F>::value == EMIT_IMAGE)
+    while (chunk > 8 && (B + chunk - 1) / chunk < 4 * (int64_t)e->num_sms) chunk >>= 1;
+  if (e->chunk_lanes > 0) chunk = e->chunk_lanes;
+  a.chunk_lanes = chunk;
+  const int64_t n_chunks = (B + chunk - 1) / chunk;
   int threads = e->block_threads;
   bool persistent = false;
   if (is_onehot && a.emit_bulk) {
@@ -99,6 +109,7 @@ int device_launch(bsb_env* e, LaunchArgs a, cudaStream_t stream) {
     int m = 1;
     while (m < 16 && (size_t)(2 * m) * tile <= 40 * 1024) m <<= 1;
     if (e->deep_sea_group > 0) m = e->deep_sea_group;
+    if (m > chunk) m = chunk;               // a group never spans chunks
     if (((size_t)m * tile) % 16 != 0 || (size_t)TILE_STAGES * m * tile > 100 * 1024) {
       a.emit_bulk = 0;                      // tiles too large (or misaligned) for the staged path: vector stores
     } else {
@@ -112,7 +123,7 @@ int device_launch(bsb_env* e, LaunchArgs a, cudaStream_t stream) {
   if (smem > 200 * 1024) return fail(BSB_UNSUPPORTED, "observation too large for the staged emitter");
   auto kernel = transition_kernel<F, RK, kNoise, kTrack>;
   if (smem > 48 * 1024) BSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int64_t grid = (B + threads - 1) / threads;
+  int64_t grid = (n_chunks + threads / 32 - 1) / (threads / 32);
   if (persistent) {
     // As many CTAs as are co-resident (shared-memory bound; 1 KB per CTA is reserved by the driver); their warps
     // draw 32-lane chunks from the environment's global counter.
@@ -142,7 +153,7 @@ int device_launch(bsb_env* e, LaunchArgs a, cudaStream_t stream) {
   BSB_CUDA(cudaLaunchKernelEx(&cfg, kernel, e->p, a));
   // chunks [warps, n_chunks) are fetched once each and every warp makes exactly one failing fetch
   // (graph-safe mode: the last CTA zeroes the counter instead)
-  if (a.work_counter && !a.clock) e->work_base += (unsigned long long)((B + 31) / 32);
+  if (a.work_counter && !a.clock) e->work_base += (unsigned long long)n_chunks;
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return BSB_OK;
 }

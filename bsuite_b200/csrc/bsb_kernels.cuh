@@ -58,6 +58,7 @@ struct LaunchArgs {
   // Null in the default mode, where `step0` / `work_base` arrive as launch arguments from the host's counters.
   unsigned long long* clock;
   int32_t no_pdl;           // set while the stream is being captured
+  int32_t chunk_lanes;      // lanes per chunk (= per warp pass): 32, or 16 / 8 when the batch would under-fill the SMs
 };
 
 enum { MODE_STEP = 0, MODE_RESET = 1, MODE_INIT = 2 };
@@ -311,7 +312,10 @@ template <> struct Descriptor<Mnist> {
 };
 
 // ----- the fused transition kernel ----------------------------------------------
-// Work unit: a CHUNK of 32 consecutive lanes, processed by one warp (thread = lane).
+// Work unit: a CHUNK of 32 consecutive lanes, processed by one warp (thread = lane).  When the batch is too small
+// to give every SM a few warps that way and the emitter walks the chunk's lanes serially (mnist images), the host
+// shrinks chunks to 16 or 8 lanes (a.chunk_lanes): the transition then idles some threads, which costs nothing
+// next to spreading 4 096 lanes x 3 KB over 512 warps instead of 128.
 //   * default launch: one chunk per warp, ceil(B / 32) warps; small CTAs (64 threads) keep the per-SM share of
 //     the 2048 chunks of a 65 536-lane batch within ~1% of even on 148 SMs and let the hardware CTA scheduler
 //     balance SMs dynamically.
@@ -374,7 +378,8 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
   int64_t step0 = a.step0;
   if (a.clock) step0 += (int64_t)*reinterpret_cast<volatile unsigned long long*>(a.clock);
 
-  const int64_t n_chunks = (B + 31) / 32;
+  const int cl = a.chunk_lanes;
+  const int64_t n_chunks = (B + cl - 1) / cl;
   const bool dynamic = a.work_counter != nullptr;
   const bool lazy = a.lazy_fetch != 0;
   // The elected lane draws chunk indices [total_warps, n_chunks) from the global counter and broadcasts them
@@ -396,10 +401,10 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
   bool any_bulk = false;
 
   while (cur_chunk < n_chunks) {
-    const int64_t warp_base = cur_chunk * 32;
+    const int64_t warp_base = cur_chunk * cl;
     // eager policy: reserve the next chunk now; lazy (default): only after this chunk's stores are issued
     cur_chunk = (dynamic && !lazy) ? fetch_chunk() : n_chunks;
-    const int n_lanes = (B - warp_base) < 32 ? (int)(B - warp_base) : 32;
+    const int n_lanes = (B - warp_base) < cl ? (int)(B - warp_base) : cl;
     const int64_t lane = warp_base + tid;
     const bool active = tid < n_lanes;
     // Bulk (TMA) emission needs 16-byte aligned spans; the choice is warp-uniform per chunk.
