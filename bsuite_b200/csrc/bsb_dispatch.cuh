@@ -79,6 +79,11 @@ void host_run(const EnvParams& p, const LaunchArgs& a) {
 }
 
 // --------------------------- device dispatch --------------------------------
+// Graph-safe mode, large grids: advances the device clock after a transition launch (see the kernel's comment).
+static __global__ void advance_clock_kernel(unsigned long long* clock, unsigned long long steps) {
+  clock[0] += steps; clock[1] = 0ull; clock[2] = 0ull;
+}
+
 template <class F, int RK, bool kNoise, bool kTrack>
 int device_launch(bsb_env* e, LaunchArgs a, cudaStream_t stream) {
   const int K = e->p.obs_numel;
@@ -137,6 +142,7 @@ int device_launch(bsb_env* e, LaunchArgs a, cudaStream_t stream) {
       persistent = false;      // everything is resident anyway: one chunk per warp
     }
   }
+  a.clock_external = (a.clock && grid > 2048) ? 1 : 0;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)grid);
@@ -151,6 +157,11 @@ int device_launch(bsb_env* e, LaunchArgs a, cudaStream_t stream) {
     cfg.numAttrs = 1;
   }
   BSB_CUDA(cudaLaunchKernelEx(&cfg, kernel, e->p, a));
+  if (a.clock_external) {
+    advance_clock_kernel<<<1, 1, 0, stream>>>(a.clock, a.mode == MODE_INIT ? 0ull : (unsigned long long)a.T);
+    BSB_CUDA(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+  }
   // chunks [warps, n_chunks) are fetched once each and every warp makes exactly one failing fetch
   // (graph-safe mode: the last CTA zeroes the counter instead)
   if (a.work_counter && !a.clock) e->work_base += (unsigned long long)n_chunks;

@@ -58,6 +58,7 @@ struct LaunchArgs {
   // Null in the default mode, where `step0` / `work_base` arrive as launch arguments from the host's counters.
   unsigned long long* clock;
   int32_t no_pdl;           // set while the stream is being captured
+  int32_t clock_external;   // graph-safe mode, large grids: a one-thread kernel enqueued after this one advances the clock
   int32_t chunk_lanes;      // lanes per chunk (= per warp pass): 32, or 16 / 8 when the batch would under-fill the SMs
 };
 
@@ -540,7 +541,7 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
     if (dynamic && lazy) cur_chunk = fetch_chunk();        // lazy: nothing was reserved while working
   }
   if (any_bulk && tid == 0) bulk_wait_read<0>();      // shared memory must outlive the last bulk read
-  if (a.clock) {
+  if (a.clock && !a.clock_external) {
     __syncthreads();
     if (threadIdx.x == 0) {
       __threadfence();

@@ -22,6 +22,9 @@ CASES = [
     ('umbrella_chain', dict(chain_length=5, n_distractor=20), 2048, 3),
     ('memory_chain', dict(memory_length=4, num_bits=3), 777, 3),
     ('mnist', dict(), 300, 2),
+    # 2 188 CTAs: above the grid size up to which the last CTA advances the device clock (a separate kernel does)
+    ('bandit', dict(mapping_seed=1), 140000, 3),
+    ('deep_sea', dict(size=6, mapping_seed=9), 80000, 2),    # persistent grid of 2 368 CTAs + external clock kernel
 ]
 
 

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Per-family throughput table on one GPU: single-step launches and T-fused rollouts.
 
-    python tools/bench_families.py [--out gpurun_out/families.jsonl] [--only catch]
+    python tools/bench_families.py [--out gpurun_out/families.jsonl] [--only catch] [--batch 4096] [--graph 16]
 
 For every configuration: env-steps/s and the algorithmic-bytes bandwidth (SURVEY.md 8d formula:
 4*obs_numel + 4 action + 4 reward + 4 discount + 4 step_type + state read/write) for
@@ -62,6 +62,7 @@ def main():
   ap.add_argument('--steps', type=int, default=60)
   ap.add_argument('--rollout', type=int, default=16)
   ap.add_argument('--batch', type=int, default=0, help='override every configuration\'s batch size')
+  ap.add_argument('--graph', type=int, default=0, help='also time G single-step launches replayed from one CUDA graph')
   args = ap.parse_args()
   mnist_dir = '/tmp/bsb_bench_mnist'
   datasets.write_synthetic_mnist(mnist_dir, 4096, 16, 0)
@@ -87,6 +88,17 @@ def main():
       T //= 2
     rbuf = env.make_buffers(T)
     roll_s = measure(lambda i=0: env.rollout(T, out=rbuf), 6, warm=2) / T
+    graph_s = None
+    if args.graph:
+      G = args.graph
+      while G > 1 and G * obs_bytes > 3e9:
+        G //= 2
+      genv = bsuite_b200.load_from_id(what, batch=batch, device='cuda', seed=0)
+      graphed = genv.capture(G)                      # G per-step launches, caller-provided actions
+      graphed.actions.copy_(acts[:G])
+      graph_s = measure(lambda i=0: graphed.replay(), max(3, args.steps // G), warm=2) / G
+      del graphed
+      genv.close()
     row = dict(name=name, batch=batch, obs_numel=numel, bytes_per_lane_step=bytes_per,
                step_us=step_s * 1e6, step_steps_per_s=batch / step_s, step_gbs=batch * bytes_per / step_s / 1e9,
                rollout_T=T, rollout_us_per_step=roll_s * 1e6, rollout_steps_per_s=batch / roll_s,
@@ -94,7 +106,10 @@ def main():
     rows.append(row)
     print(f"{name:32s} B={batch:8d} K={numel:5d}  step {row['step_us']:8.1f} us {row['step_steps_per_s']:.3e}/s "
           f"{row['step_gbs']:7.0f} GB/s | rollout(T={T}) {row['rollout_us_per_step']:8.1f} us/step "
-          f"{row['rollout_steps_per_s']:.3e}/s {row['rollout_gbs']:7.0f} GB/s", flush=True)
+          f"{row['rollout_steps_per_s']:.3e}/s {row['rollout_gbs']:7.0f} GB/s"
+          + ('' if graph_s is None else f" | graph {graph_s * 1e6:7.1f} us/step"), flush=True)
+    if graph_s is not None:
+      row.update(graph_us_per_step=graph_s * 1e6, graph_steps_per_s=batch / graph_s)
     env.close()
     del ring, rbuf, acts
     torch.cuda.empty_cache()
