@@ -146,6 +146,7 @@ int validate(const bsb_config& c, int64_t batch, int* obs_rows, int* obs_cols, i
       *obs_rows = 1; *obs_cols = 2; *n_actions = 5; break;
     case BSB_MNIST:
       if (c.num_data < 1 || c.image_rows < 1 || c.image_cols < 1) return fail(BSB_INVALID_ARGUMENT, "mnist needs num_data, image_rows, image_cols");
+      if (c.image_rows > 4096 || c.image_cols > 4096) return fail(BSB_UNSUPPORTED, "mnist image sides must be <= 4096");
       if (!c.table || c.table_bytes != (int64_t)c.num_data * c.image_rows * c.image_cols) return fail(BSB_INVALID_ARGUMENT, "mnist needs an int8 image table");
       if (!c.table2 || c.table2_bytes != c.num_data) return fail(BSB_INVALID_ARGUMENT, "mnist needs a uint8 label table");
       *obs_rows = c.image_rows; *obs_cols = c.image_cols; *n_actions = 10; break;
@@ -289,7 +290,7 @@ int32_t bsb_create(const bsb_config* config, int64_t batch, int32_t device, uint
   p.family = c.family; p.wrapper = c.wrapper; p.rng_kind = c.rng_kind; p.flags = c.flags;
   p.size = c.size; p.deterministic = c.deterministic; p.rows = c.rows; p.columns = c.columns;
   p.memory_length = c.memory_length; p.num_bits = c.num_bits; p.chain_length = c.chain_length; p.n_distractor = c.n_distractor;
-  p.num_actions = n_actions; p.max_steps = c.max_steps; p.num_data = c.num_data; p.image_numel = c.image_rows * c.image_cols;
+  p.num_actions = n_actions; p.max_steps = c.max_steps; p.num_data = c.num_data; p.image_numel = c.family == BSB_MNIST ? c.image_rows * c.image_cols : 0;
   p.obs_rows = obs_rows; p.obs_cols = obs_cols; p.obs_numel = obs_rows * obs_cols; p.n_info = e->names.n;
   p.batch = batch; p.seed = seed; p.lane_offset = lane_offset;
   if (c.family == BSB_DEEP_SEA) { p.move_cost_step = c.unscaled_move_cost / (double)c.size; p.inv_size = 1.0 / (double)c.size; }

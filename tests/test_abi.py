@@ -125,3 +125,14 @@ def test_raw_abi_round_trip_without_torch():
   assert set(regret.tolist()) <= {0.0, 2.0}
   assert lib.bsb_read_info(handle, 5, ctypes.c_void_p(regret.ctypes.data), None) == 1
   _lib.check(lib.bsb_destroy(handle))
+
+
+def test_abi_fuzzer_finds_no_crash():
+  """A short run of tools/fuzz_abi.py (hostile configurations and argument misuse on the host path); the long run
+  under ASan/UBSan is tools/host_sanitize.sh."""
+  import subprocess
+  import sys
+  proc = subprocess.run([sys.executable, os.path.join(cf.ROOT, 'tools', 'fuzz_abi.py'), '300', '7'],
+                        capture_output=True, text=True, timeout=300)
+  assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-2000:]
+  assert 'no crash' in proc.stdout

@@ -1,7 +1,8 @@
 #!/bin/bash
 # AddressSanitizer + UndefinedBehaviorSanitizer over the HOST side of the library (handle management, the explicit
 # host path of every family, the C ABI): builds a sanitized copy of libbsuite_b200.so under /tmp and runs the whole
-# CPU test-suite against it (BSB_LIBRARY points the ctypes binding at that build).  No GPU needed.
+# CPU test-suite and the ABI fuzzer (tools/fuzz_abi.py) against it (BSB_LIBRARY points the ctypes binding at that
+# build).  No GPU needed.
 #   bash tools/host_sanitize.sh [logfile]
 set -e
 OUT=/tmp/bsb_asan
@@ -17,5 +18,8 @@ LD_PRELOAD="$(gcc -print-file-name=libasan.so) $(gcc -print-file-name=libubsan.s
   UBSAN_OPTIONS=print_stacktrace=1 BSB_LIBRARY=$OUT/libbsuite_b200.so \
   python -m pytest tests -q -m "not gpu" -p no:cacheprovider > "$LOG" 2>&1
 echo "pytest rc=$?" >> "$LOG"
+LD_PRELOAD="$(gcc -print-file-name=libasan.so) $(gcc -print-file-name=libubsan.so)" ASAN_OPTIONS=detect_leaks=0 \
+  UBSAN_OPTIONS=print_stacktrace=1 BSB_LIBRARY=$OUT/libbsuite_b200.so python tools/fuzz_abi.py 3000 0 >> "$LOG" 2>&1
+echo "fuzz rc=$?" >> "$LOG"
 echo "sanitizer reports: $(grep -c 'runtime error\|AddressSanitizer' "$LOG")" >> "$LOG"
-tail -3 "$LOG"
+tail -5 "$LOG"
