@@ -81,9 +81,10 @@ class SweepBatch:
     block = self.local_returns()
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
       world = dist.get_world_size()
-      out = torch.empty((world,) + tuple(block.shape), dtype=block.dtype, device=block.device)
-      dist.all_gather_into_tensor(out, block.contiguous())
-      return out
+      flat = block.contiguous().reshape(-1)        # 1-D in, 1-D out: the one layout every backend accepts
+      out = torch.empty(world * flat.numel(), dtype=block.dtype, device=block.device)
+      dist.all_gather_into_tensor(out, flat)
+      return out.reshape((world,) + tuple(block.shape))
     return block.unsqueeze(0)
 
   def bytes_per_step(self) -> int:

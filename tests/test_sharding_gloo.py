@@ -76,3 +76,34 @@ def test_shard_range_covers_batch():
     assert all(spans[i][0] + spans[i][1] == spans[i + 1][0] for i in range(world - 1))
   with pytest.raises(ValueError):
     bd.shard_range(4, 4, 4)
+
+
+SWEEP_IDS = ['catch/0', 'deep_sea/0', 'memory_len/3', 'bandit_noise/2']
+
+
+def _sweep_worker(rank, world, port, out_dir):
+  sys.path.insert(0, ROOT)
+  os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+  dist.init_process_group('gloo', rank=rank, world_size=world)
+  from bsuite_b200 import suite
+  batch = suite.SweepBatch(SWEEP_IDS, lanes=10, device='cpu', seed=SEED, rank=rank, world=world)
+  batch.rollout(40, action_seed=9)
+  gathered = batch.gather_returns()                    # [world, n_ids, 3]
+  np.save(os.path.join(out_dir, f'sweep{rank}.npy'), gathered.numpy())
+  dist.destroy_process_group()
+
+
+def test_two_rank_sweep_batch_gathers_what_one_rank_computes(tmp_path):
+  """BASELINE config #5 across ranks: every id's lanes are split over the ranks (global lane ids key the RNG and the
+  on-device action stream), and the all-gather of the per-id Logging sums adds up to the single-rank sums."""
+  from bsuite_b200 import suite
+  world, port = 2, _free_port()
+  mp.spawn(_sweep_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+  whole = suite.SweepBatch(SWEEP_IDS, lanes=10, device='cpu', seed=SEED)
+  whole.rollout(40, action_seed=9)
+  want = whole.gather_returns().numpy()[0]              # [n_ids, 3]
+  blocks = [np.load(tmp_path / f'sweep{r}.npy') for r in range(world)]
+  np.testing.assert_array_equal(blocks[0], blocks[1])    # every rank holds the same gathered tensor
+  assert blocks[0].shape == (world, len(SWEEP_IDS), 3)
+  np.testing.assert_allclose(blocks[0].sum(axis=0), want, rtol=0, atol=1e-9)
+  assert np.all(want[:, 2] > 0)                          # steps were taken for every id
