@@ -108,3 +108,40 @@ def test_reference_csv_load_reads_our_files(tmp_path):
   df_ref, _ = csv_load.load_bsuite(ref_dir)
   columns = ['steps', 'episode', 'total_return', 'episode_len', 'episode_return', 'total_regret', 'bsuite_id']
   assert df_ours[columns].reset_index(drop=True).equals(df_ref[columns].reset_index(drop=True))
+
+
+def test_terminal_logger_formats_like_the_reference():
+  """`k1 = v1 | k2 = v2`, keys sorted, integers plain, other numbers with 4 decimals (terminal_logging.py:57-74);
+  compared with the reference's own formatter when it is importable."""
+  data = {'steps': 12, 'total_return': -3.0, 'episode': np.int64(4), 'episode_return': np.float64(0.123456),
+          'name': 'catch/0', 'flag': True}
+  lines = []
+  recording.TerminalLogger(print_fn=lines.append).write(data)
+  assert lines == ['episode = 4 | episode_return = 0.1235 | flag = True | name = catch/0 | steps = 12 | total_return = -3.0000']
+  raw = []
+  recording.TerminalLogger(pretty_print=False, print_fn=raw.append).write(data)
+  assert raw == [data]
+  if rr.reference_available():
+    rr.import_reference()
+    from bsuite.logging import terminal_logging  # pylint: disable=import-outside-toplevel
+    assert terminal_logging.pretty_dict(data) == lines[0]
+
+
+def test_load_and_record_modes(tmp_path, capsys):
+  """bsuite.load_and_record (bsuite.py:111-123): 'csv' and 'terminal' modes, ValueError otherwise."""
+  env = bsuite_b200.load_and_record('bandit/0', str(tmp_path), logging_mode='csv', device='cpu')
+  assert isinstance(env, recording.Recorder) and env.bsuite_num_episodes > 0
+  env.reset()
+  env.step(0)
+  env.flush()
+  assert [f.name for f in tmp_path.iterdir()] == ['bsuite_id_-_bandit-0.csv']
+  with pytest.raises(ValueError):        # the reference refuses to overwrite existing results (csv_logging.py:77-80)
+    bsuite_b200.load_and_record_to_csv('bandit/0', str(tmp_path), device='cpu')
+  bsuite_b200.load_and_record_to_csv('bandit/0', str(tmp_path), overwrite=True, device='cpu')
+  terminal = bsuite_b200.load_and_record('bandit/0', str(tmp_path), logging_mode='terminal', device='cpu')
+  terminal.reset()
+  terminal.step(1)                        # episode 1 is a log point (wrappers.py:140-147)
+  printed = capsys.readouterr().out
+  assert 'episode = 1 |' in printed and 'total_regret = ' in printed
+  with pytest.raises(ValueError, match='Unrecognised logging_mode'):
+    bsuite_b200.load_and_record('bandit/0', str(tmp_path), logging_mode='sqlite', device='cpu')
