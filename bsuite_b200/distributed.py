@@ -38,15 +38,17 @@ def load_sharded(bsuite_id: str, global_batch: int, rank: Optional[int] = None, 
 
 
 def gather_episode_returns(env, group=None) -> Dict[str, Any]:
-  """One all-gather of the per-rank reduction of the Logging columns (utils/wrappers.py:113-125).
+  """One all-gather of the per-rank reduction of the Logging columns (utils/wrappers.py:113-125), synchronous on
+  the current stream (`LogPoint` is the asynchronous form).
 
   Returns tensors of shape [world]: per-rank sums of `steps`, `episode`, `total_return` and the lane count, from
   which the global mean return per episode (the quantity bsuite's analysis consumes) follows.
   """
   import torch
   import torch.distributed as dist
-  sums = env.episode_stat_sums()            # device-side reduction: (steps, episode, total_return, len, return)
-  block = torch.cat([sums[:3], torch.tensor([float(env.batch)], dtype=torch.float64, device=sums.device)])
+  block = torch.empty(6, dtype=torch.float64, device=env.device)
+  env.episode_stat_sums(out=block[:5])      # device-side reduction: (steps, episode, total_return, len, return)
+  block[5:].fill_(float(env.batch))
   if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
     world = dist.get_world_size(group)
     gathered = torch.empty(world * block.numel(), dtype=block.dtype, device=block.device)
@@ -54,7 +56,87 @@ def gather_episode_returns(env, group=None) -> Dict[str, Any]:
     gathered = gathered.view(world, block.numel())
   else:
     gathered = block.view(1, -1)
-  return dict(steps=gathered[:, 0], episode=gathered[:, 1], total_return=gathered[:, 2], lanes=gathered[:, 3])
+  return dict(steps=gathered[:, 0], episode=gathered[:, 1], total_return=gathered[:, 2], lanes=gathered[:, 5])
+
+
+class LogPoint:
+  """Asynchronous log point for one or more tracked environments ("off the critical path").
+
+  The reference writes a log row at log-spaced episode counts (utils/wrappers.py:99-110, 140-147): log points
+  are rare, and nothing on the step path waits for them.  Here a log point is
+    1. one reduction kernel per environment on the CALLER'S stream, in order with the steps it summarises,
+       writing the five Logging sums straight into a row of a preallocated block (no allocation, no indexing);
+    2. an event; a SIDE stream waits for it and runs the one collective of the path (all-gather of the block,
+       40 bytes per environment and rank, NCCL on GPUs) into a preallocated buffer;
+  so the caller's stream goes on launching steps k+1... immediately.  `issue()` returns a ticket; `result(ticket)`
+  makes the caller's stream (default) or the host wait for that gather and returns `[world, n_envs, 5]` with the
+  columns (steps, episode, total_return, episode_len, episode_return).  `slots` tickets can be in flight.
+  """
+
+  COLUMNS = ('steps', 'episode', 'total_return', 'episode_len', 'episode_return')
+
+  def __init__(self, envs, group=None, slots: int = 2):
+    import torch
+    import torch.distributed as dist
+    self._torch, self._dist, self._group = torch, dist, group
+    self.envs = list(envs) if isinstance(envs, (list, tuple)) else [envs]
+    self._device = self.envs[0].device
+    self._cuda = self._device.type == 'cuda'
+    self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    n = len(self.envs)
+    self._slots = int(slots)
+    self._local = torch.zeros((self._slots, n, 5), dtype=torch.float64, device=self._device)
+    self._gathered = (torch.zeros((self._slots, self.world, n, 5), dtype=torch.float64, device=self._device)
+                      if self.world > 1 else None)
+    self._side = torch.cuda.Stream(device=self._device) if (self._cuda and self.world > 1) else None
+    self._ready = [torch.cuda.Event() for _ in range(self._slots)] if self._side is not None else None
+    self._done = [torch.cuda.Event() for _ in range(self._slots)] if self._cuda else None
+    self._issued = 0
+
+  def issue(self) -> int:
+    torch = self._torch
+    ticket = self._issued
+    slot = ticket % self._slots
+    self._issued += 1
+    current = torch.cuda.current_stream(self._device) if self._cuda else None
+    if self._side is not None and ticket >= self._slots:
+      current.wait_event(self._done[slot])          # the gather that last read this slot's block has finished
+    block = self._local[slot]
+    for i, env in enumerate(self.envs):
+      env.episode_stat_sums(out=block[i])
+    if self.world == 1:
+      if self._cuda:
+        self._done[slot].record(current)
+      return ticket
+    flat_in, flat_out = block.view(-1), self._gathered[slot].view(-1)
+    if self._side is None:                           # host tensors (gloo): nothing to overlap with
+      self._dist.all_gather_into_tensor(flat_out, flat_in, group=self._group)
+      return ticket
+    self._ready[slot].record(current)
+    with torch.cuda.stream(self._side):
+      self._side.wait_event(self._ready[slot])
+      self._dist.all_gather_into_tensor(flat_out, flat_in, group=self._group)
+      self._done[slot].record(self._side)
+    return ticket
+
+  def result(self, ticket: int, host_sync: bool = False):
+    """`[world, n_envs, 5]` of `ticket` (valid until `slots` further tickets have been issued)."""
+    if not self._issued - self._slots <= ticket < self._issued:
+      raise ValueError(f'ticket {ticket} is not in flight (issued {self._issued}, slots {self._slots})')
+    slot = ticket % self._slots
+    if self._cuda:
+      if host_sync:
+        self._done[slot].synchronize()
+      else:
+        self._torch.cuda.current_stream(self._device).wait_event(self._done[slot])
+    return self._local[slot].unsqueeze(0) if self.world == 1 else self._gathered[slot]
+
+  def join(self):
+    """Makes the caller's stream wait for every gather in flight (e.g. before closing a timed region)."""
+    if self._cuda:
+      current = self._torch.cuda.current_stream(self._device)
+      for t in range(max(0, self._issued - self._slots), self._issued):
+        current.wait_event(self._done[t % self._slots])
 
 
 def gather_lane_tensor(tensor, group=None):

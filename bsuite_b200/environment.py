@@ -194,6 +194,7 @@ class BatchedEnvironment:
   seed = property(lambda self: self._seed)
   lane_offset = property(lambda self: self._lane_offset)
   obs_shape = property(lambda self: self._spec.obs_shape)
+  family = property(lambda self: self._spec.family)
   num_actions = property(lambda self: self._spec.num_actions)
   info_names = property(lambda self: self._info_names)
 
@@ -411,14 +412,20 @@ class BatchedEnvironment:
       result[name] = dst
     return result
 
-  def episode_stat_sums(self):
+  def episode_stat_sums(self, out=None):
     """Sums over this environment's lanes of (steps, episode, total_return, episode_len, episode_return): a float64
-    tensor [5] on the environment's device, produced by ONE reduction kernel (`bsb_sum_episode_stats`)."""
+    tensor [5] on the environment's device, produced by ONE reduction kernel (`bsb_sum_episode_stats`).  `out`
+    (contiguous float64 [5] on the same device, e.g. a row of a preallocated log-point block) receives the sums
+    in place, so a log point allocates nothing."""
     if not self._track:
       raise RuntimeError('create the environment with track_episodes=True')
-    dst = self._torch.empty(5, dtype=self._torch.float64, device=self._device)
-    _lib.check(self._lib.bsb_sum_episode_stats(self._handle.ptr, dst.data_ptr(), self._stream()))
-    return dst
+    torch = self._torch
+    if out is None:
+      out = torch.empty(5, dtype=torch.float64, device=self._device)
+    elif not (out.dtype is torch.float64 and out.numel() == 5 and out.is_contiguous() and out.device == self._device):
+      raise ValueError('out must be a contiguous float64 tensor of 5 elements on the environment\'s device')
+    _lib.check(self._lib.bsb_sum_episode_stats(self._handle.ptr, out.data_ptr(), self._stream()))
+    return out
 
   # ---- checkpoint ------------------------------------------------------------
   def state_dict(self) -> Dict[str, Any]:

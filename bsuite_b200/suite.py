@@ -20,10 +20,22 @@ def one_per_experiment(setting: int = 0) -> List[str]:
   return [ids[min(setting, len(ids) - 1)] for ids in sweep.BY_EXPERIMENT.values()]
 
 
+# Compact lane state read + written per lane-step by family id (deep_sea / catch one packed word,
+# cartpole / swingup 5 x f64, mountain_car 2 x f64 + the step word, the rest a word + an 8-byte RNG position).
+_STATE_BYTES = {0: 8, 1: 8, 2: 80, 3: 80, 4: 48}
+
+
+def algorithmic_bytes_per_lane_step(env) -> int:
+  numel = 1
+  for d in env.obs_shape:
+    numel *= d
+  return 4 * numel + 16 + _STATE_BYTES.get(env.family, 16)
+
+
 class SweepBatch:
 
   def __init__(self, bsuite_ids: Optional[Sequence[str]] = None, lanes: int = 4096, device='cuda', seed: int = 0,
-               rank: int = 0, world: int = 1, track_episodes: bool = True):
+               rank: int = 0, world: int = 1, track_episodes: bool = True, ring: int = 1):
     import torch
     self._torch = torch
     self.bsuite_ids = list(bsuite_ids) if bsuite_ids is not None else one_per_experiment()
@@ -37,65 +49,85 @@ class SweepBatch:
     self._device = next(iter(self.envs.values())).device
     self._cuda = self._device.type == 'cuda'
     self._streams = {k: torch.cuda.Stream(device=self._device) for k in self.envs} if self._cuda else {}
+    self._ring = max(1, int(ring))      # output buffer sets cycled through by successive rollouts (> L2 when timing)
+    self._turn = 0
     self._buffers: Dict[str, object] = {}
     self._buffer_steps = None
+    self._lp = None
+    self._cols = None
 
   def _ensure_buffers(self, num_steps: int):
     if self._buffer_steps != num_steps:
-      self._buffers = {k: env.make_buffers(num_steps, with_actions=True) for k, env in self.envs.items()}
+      self._buffers = {}
+      self._buffers = {k: [env.make_buffers(num_steps, with_actions=True) for _ in range(self._ring)]
+                       for k, env in self.envs.items()}
       self._buffer_steps = num_steps
 
   def rollout(self, num_steps: int, action_seed: int = 0):
     """`num_steps` fused steps of every environment (on-device uniform random actions); returns id -> TimeStep.
 
-    The returned tensors are reused by the next call.  On CUDA each environment runs on its own stream; the
+    The returned tensors are reused `ring` calls later.  On CUDA each environment runs on its own stream; the
     caller's current stream waits for all of them before this function returns control of the outputs.
     """
     torch = self._torch
     self._ensure_buffers(num_steps)
+    slot = self._turn % self._ring
+    self._turn += 1
     result = {}
     if not self._cuda:
       for k, env in self.envs.items():
-        result[k] = env.rollout(num_steps, action_seed=action_seed, out=self._buffers[k])
+        result[k] = env.rollout(num_steps, action_seed=action_seed, out=self._buffers[k][slot])
       return result
     current = torch.cuda.current_stream(self._device)
     for k, env in self.envs.items():
       stream = self._streams[k]
       stream.wait_stream(current)
       with torch.cuda.stream(stream):
-        result[k] = env.rollout(num_steps, action_seed=action_seed, out=self._buffers[k])
+        result[k] = env.rollout(num_steps, action_seed=action_seed, out=self._buffers[k][slot])
     for stream in self._streams.values():
       current.wait_stream(stream)
     return result
 
+  def set_ring(self, ring: int):
+    """Number of output buffer sets successive rollouts cycle through (drops the current buffers)."""
+    self._ring = max(1, int(ring))
+    self._buffers, self._buffer_steps = {}, None
+
+  def last_buffers(self, bsuite_id: str):
+    """The `StepBuffers` (outputs + the actions sampled on the device) the latest rollout of `bsuite_id` wrote."""
+    return self._buffers[bsuite_id][(self._turn - 1) % self._ring]
+
+  def _log_point(self):
+    if self._lp is None:
+      self._lp = distributed.LogPoint(list(self.envs.values()))
+      self._cols = self._torch.tensor([2, 1, 0], device=self._device)     # (total_return, episode, steps)
+    return self._lp
+
+  def issue_log_point(self) -> int:
+    """Asynchronous log point (`distributed.LogPoint`): one reduction kernel per id on the current stream, writing
+    into a preallocated block; the all-gather runs on a side stream, so further rollouts are not held up."""
+    return self._log_point().issue()
+
+  def log_point_result(self, ticket: int, host_sync: bool = False):
+    """float64 [world, n_ids, 3]: per-rank, per-id sums of (total_return, episode, steps) of `ticket`."""
+    return self._log_point().result(ticket, host_sync=host_sync).index_select(-1, self._cols)
+
   def local_returns(self):
     """float64 [n_ids, 3] on the device: per-id sums of (total_return, episode, steps) over this rank's lanes."""
     torch = self._torch
-    sums = torch.stack([env.episode_stat_sums() for env in self.envs.values()])   # one reduction kernel per id
-    return sums[:, [2, 1, 0]]
+    block = torch.empty((len(self.envs), 5), dtype=torch.float64, device=self._device)
+    for i, env in enumerate(self.envs.values()):
+      env.episode_stat_sums(out=block[i])                     # one reduction kernel per id, written in place
+    return block.index_select(-1, self._log_point() and self._cols)
 
   def gather_returns(self):
-    """The one collective of the path: all-gather of `local_returns()`; returns [world, n_ids, 3]."""
-    torch = self._torch
-    import torch.distributed as dist
-    block = self.local_returns()
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-      world = dist.get_world_size()
-      flat = block.contiguous().reshape(-1)        # 1-D in, 1-D out: the one layout every backend accepts
-      out = torch.empty(world * flat.numel(), dtype=block.dtype, device=block.device)
-      dist.all_gather_into_tensor(out, flat)
-      return out.reshape((world,) + tuple(block.shape))
-    return block.unsqueeze(0)
+    """The one collective of the path, synchronous form: returns [world, n_ids, 3] (see `issue_log_point`)."""
+    return self.log_point_result(self.issue_log_point())
 
   def bytes_per_step(self) -> int:
-    """Algorithmic bytes of one lock-step of the whole local batch (obs + 16 B of scalars per lane; state excluded)."""
-    total = 0
-    for env in self.envs.values():
-      numel = 1
-      for d in env.obs_shape:
-        numel *= d
-      total += env.batch * (4 * numel + 16)
-    return total
+    """Algorithmic bytes of one lock-step of the whole local batch (dense observation + action +
+    reward + discount + step_type + compact lane state read and written)."""
+    return sum(env.batch * algorithmic_bytes_per_lane_step(env) for env in self.envs.values())
 
   def close(self):
     for env in self.envs.values():

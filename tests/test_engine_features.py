@@ -222,3 +222,25 @@ def test_episode_stat_sums_need_tracking():
   env = bsuite_b200.make('catch', batch=4, device='cpu')
   with pytest.raises(RuntimeError):
     env.episode_stat_sums()
+
+
+@pytest.mark.gpu
+def test_async_log_point_equals_the_synchronous_reduction_on_cuda():
+  """distributed.LogPoint: reduction in stream order, result through the ticket; steps issued AFTER the log point
+  must not leak into it (the block is a snapshot), and slots are reused safely."""
+  import torch
+  from bsuite_b200 import distributed as bd
+  envs = [bsuite_b200.load_from_id(i, batch=4096, device='cuda', seed=5, track_episodes=True) for i in ('catch/0', 'deep_sea/0')]
+  lp = bd.LogPoint(envs, slots=2)
+  for round_ in range(6):
+    for env in envs:
+      env.rollout(9, action_seed=round_)
+    want = torch.stack([env.episode_stat_sums() for env in envs])
+    ticket = lp.issue()
+    for env in envs:                      # work queued behind the log point
+      env.rollout(3, action_seed=100 + round_)
+    got = lp.result(ticket, host_sync=(round_ % 2 == 0))
+    torch.cuda.synchronize()
+    assert got.shape == (1, 2, 5) and torch.equal(got[0], want)
+  for env in envs:
+    env.close()

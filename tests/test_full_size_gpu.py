@@ -155,7 +155,7 @@ def test_mixed_float_dynamics_batch():
   for bsuite_id, env_class in (('cartpole/0', 'cartpole'), ('mountain_car/0', 'mountain_car')):
     ts = result[bsuite_id]
     assert tuple(ts.observation.shape)[:2] == (T, lanes) and bool(torch.isfinite(ts.observation).all())
-    actions = batch._buffers[bsuite_id].actions.cpu().numpy()   # pylint: disable=protected-access
+    actions = batch.last_buffers(bsuite_id).actions.cpu().numpy()   # pylint: disable=protected-access
     for lane in _sample_lanes(lanes, count=12):
       want = oracle.run_lanes(env_class, {}, actions[:, lane:lane + 1], seed=seed, lane_offset=int(lane))
       np.testing.assert_array_equal(ts.step_type[:, lane].cpu().numpy(), want['step_type'][:, 0])

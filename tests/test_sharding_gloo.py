@@ -107,3 +107,21 @@ def test_two_rank_sweep_batch_gathers_what_one_rank_computes(tmp_path):
   assert blocks[0].shape == (world, len(SWEEP_IDS), 3)
   np.testing.assert_allclose(blocks[0].sum(axis=0), want, rtol=0, atol=1e-9)
   assert np.all(want[:, 2] > 0)                          # steps were taken for every id
+
+
+def test_async_log_point_matches_the_synchronous_gather_on_host():
+  """distributed.LogPoint (ticketed, slot-reusing) returns exactly what the synchronous reduction returns."""
+  import torch
+  import bsuite_b200
+  from bsuite_b200 import distributed as bd
+  envs = [bsuite_b200.load_from_id(i, batch=24, device='cpu', seed=3, track_episodes=True) for i in ('catch/0', 'bandit/0')]
+  lp = bd.LogPoint(envs, slots=2)
+  tickets = []
+  for round_ in range(5):
+    for env in envs:
+      env.rollout(7, action_seed=round_)
+    tickets.append((lp.issue(), torch.stack([env.episode_stat_sums() for env in envs])))
+    ticket, want = tickets[-1]
+    assert torch.equal(lp.result(ticket)[0], want)
+  with pytest.raises(ValueError):
+    lp.result(tickets[0][0])            # slot long since reused

@@ -45,7 +45,7 @@ def test_sweep_batch_matches_oracle_per_id(device, mnist_dir):
     np.testing.assert_allclose(float(returns[0, k, 1]), float((st == 2).sum()))
     if bsuite_id in _SETTING0:
       env_class, kwargs, wrapper, arg = _SETTING0[bsuite_id]
-      actions = batch._buffers[bsuite_id].actions.cpu().numpy()   # pylint: disable=protected-access
+      actions = batch.last_buffers(bsuite_id).actions.cpu().numpy()   # pylint: disable=protected-access
       want = oracle.run_lanes(env_class, kwargs, actions[:, :6], seed=seed, wrapper=wrapper, wrapper_arg=arg)
       np.testing.assert_array_equal(st[:, :6], want['step_type'])
       np.testing.assert_array_equal(ts.observation.cpu().numpy()[:, :6], want['observation'])
