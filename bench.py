@@ -291,21 +291,56 @@ def family_leg(name, ids, lanes, rank, world, device, torch, dist, peak_gbs, rol
       dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return _median([float(x) for x in t]) * 1e-3 / (n * T)
 
-  step_s = timed(1, iters)
+  step_s = timed(1, iters)                 # eager: one launch per id and step through the Python face
+
   T = rollout_T
   while T > 1 and T * obs_bytes * 1 > 8e9:
     T //= 2
   batch.set_ring(1 if T * obs_bytes > 300e6 else ring)
   roll_s = timed(T, max(3, iters // T))
+  # the same lock-step captured ONCE into a CUDA graph (every id's launch on its own branch) and replayed
+  graphed = batch.capture(1, lock_steps=ring)
+  def timed_graph(n, windows=3):
+    times = []
+    for _ in range(3):
+      graphed.replay()
+    torch.cuda.synchronize()
+    for _ in range(windows):
+      if world > 1:
+        dist.barrier()
+      torch.cuda.synchronize()
+      e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      e0.record()
+      for _ in range(n):
+        graphed.replay()
+        if gather:
+          batch.issue_log_point()
+      if gather:
+        batch._log_point().join()          # pylint: disable=protected-access
+      e1.record()
+      torch.cuda.synchronize()
+      times.append(e0.elapsed_time(e1))
+    t = torch.tensor(times, dtype=torch.float64, device=device)
+    if world > 1:
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return _median([float(x) for x in t]) * 1e-3 / (n * ring)
+  graph_s = timed_graph(max(3, iters // ring))
+  del graphed
   total_lanes = len(ids) * lanes
   result = {
       'ids': len(ids), 'lanes_per_id': lanes, 'global_lanes': total_lanes, 'lanes_per_gpu': total_lanes // world,
       'step_us': step_s * 1e6, 'step_value': total_lanes / step_s,
-      'step_frac': world * bytes_per_lockstep / step_s / 1e9 / (world * peak_gbs),
+      'step_frac': bytes_per_lockstep / step_s / 1e9 / peak_gbs,
+      'graph_step_us': graph_s * 1e6, 'graph_step_value': total_lanes / graph_s,
+      'graph_step_frac': bytes_per_lockstep / graph_s / 1e9 / peak_gbs,
       'rollout_T': T, 'rollout_us': roll_s * 1e6, 'rollout_value': total_lanes / roll_s,
-      'frac': world * bytes_per_lockstep / roll_s / 1e9 / (world * peak_gbs),
+      'frac': bytes_per_lockstep / roll_s / 1e9 / peak_gbs,
       'algorithmic_bytes_per_lockstep_per_gpu': bytes_per_lockstep, 'parity_sampled': bool(parity),
       'gather': bool(gather), 'ring': ring, 'unit': 'env-steps/s',
+      'note': 'step: eager single-step launches (one per id, ids on concurrent streams); graph_step: the same lock-step '
+              'replayed from one CUDA graph; rollout: T fused steps per launch with on-device actions; *_frac against '
+              'hbm_gbs with SURVEY 8d algorithmic bytes; single-step outputs cycle through `ring` buffer sets (> L2), '
+              'eagerly and under graph replay (`ring` lock-steps per graph)',
   }
   batch.close()
   del batch
@@ -448,19 +483,20 @@ def engine_main(args):
   host_actions = torch.randint(0, 2, (Ke, B), dtype=torch.int32).pin_memory()
   host_small = env.make_host_buffers(with_observation=False)
 
-  def e2e_loop(n, host):
+  def e2e_loop(n, host, prelaunch):
     for t in range(n):
-      env.step_host(host_actions[t % Ke], host, out=ring[t % RING])
+      env.step_host(host_actions[t % Ke], host, out=ring[t % RING], prelaunch=prelaunch)
+    env.host_flush()
 
-  def timed_e2e(n, host, reps):
-    e2e_loop(3, host)
+  def timed_e2e(n, host, reps, prelaunch=False):
+    e2e_loop(3, host, prelaunch)
     secs = []
     for _ in range(reps):
       if world > 1:
         dist.barrier()
       torch.cuda.synchronize()
       t0 = time.perf_counter()
-      e2e_loop(n, host)
+      e2e_loop(n, host, prelaunch)
       torch.cuda.synchronize()
       secs.append(time.perf_counter() - t0)
     dt = torch.tensor(secs, dtype=torch.float64, device=device)
@@ -468,7 +504,10 @@ def engine_main(args):
       dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     return world * B * n / _median([float(x) for x in dt]), [world * B * n / float(x) for x in dt]
 
-  e2e_value, e2e_windows = timed_e2e(Ke, host_small, WINDOWS)
+  # headline: the host-policy loop (prelaunch=True): every call rings the doorbell of a kernel that is already
+  # resident and queues the next one; `launch_per_step_value` is the same call without the pre-launch
+  e2e_value, e2e_windows = timed_e2e(Ke, host_small, WINDOWS, prelaunch=True)
+  e2e_plain, _ = timed_e2e(Ke, host_small, 3, prelaunch=False)
 
   # The same host-memory traffic WITHOUT a host synchronise per step (actions that do not depend on the previous
   # result, as in this random-action workload): env.step() given a pinned host action tensor and outputs whose
@@ -601,14 +640,20 @@ def engine_main(args):
                      'launch_us': launch_s * 1e6, 'kernel': KERNEL_NAME},
         'cpu_baseline': cpu_baseline,
         'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 4 * B, 'd2h_bytes_per_step': 12 * B,
-                'steps': Ke, 'windows': e2e_windows, 'host_obs_value': host_obs_value, 'pipelined_value': e2e_pipelined,
+                'steps': Ke, 'windows': e2e_windows, 'launch_per_step_value': e2e_plain,
+                'host_obs_value': host_obs_value, 'pipelined_value': e2e_pipelined,
                 'host_obs_d2h_bytes_per_step': 4 * B * SIZE * SIZE + 12 * B,
-                'note': 'BatchedEnvironment.step_host -> bsb_step_host every step: actions come from pinned host memory and '
-                        'reward/discount/step_type land in pinned host memory (read / written in place over PCIe by the '
-                        'kernel: zero-copy), the call returns when they have landed; observations stay on the device '
-                        '(the API contract). host_obs_value also copies the observations to pinned host memory every '
-                        'step. pipelined_value: the same per-step host traffic through env.step() with pinned actions '
-                        'and pinned scalar outputs, launches queued, one synchronise at the end.'},
+                'note': 'BatchedEnvironment.step_host(prelaunch=True) -> bsb_step_host(BSB_HOST_PRELAUNCH) every step, the '
+                        'call pattern of a host-side policy: actions come from pinned host memory and reward / discount / '
+                        'step_type land in pinned host memory (read / written in place over PCIe by the kernel: '
+                        'zero-copy); each call hands the buffers to a kernel that is already resident (doorbell in pinned '
+                        'memory), queues the next step\'s kernel and returns when this step\'s results have landed '
+                        '(completion word in pinned memory, no stream synchronise); observations stay on the device '
+                        '(the API contract). launch_per_step_value: the same call without the pre-launch (one kernel '
+                        'launch per call, completion through the mailbox). host_obs_value also copies the observations '
+                        'to pinned host memory every step. pipelined_value: the same per-step host traffic through '
+                        'env.step() with pinned actions and pinned scalar outputs, launches queued, one synchronise at '
+                        'the end.'},
         'gpu_launches': int(launches),
         'fused_rollout': fused,
         'graph_replay': graph_replay,

@@ -63,8 +63,9 @@ void host_run(const EnvParams& p, const LaunchArgs& a) {
                            : action_stream.sample(a.action_seed, p.lane_offset + (uint64_t)lane, (uint64_t)(a.step0 + t), p.num_actions);
         if (a.actions_out) a.actions_out[off] = action;
       }
+      const bool after_last = L.nr != 0;
       const StepOut o = lane_transition<F, R, R>(p, lane, L, rng, wrng, action, a.mode, noise);
-      if (track) ep.track(p, lane, o, a.step0 + t);
+      if (track) ep.track(p, lane, o, a.step0 + t, after_last);
       if (a.reward) a.reward[off] = (float)o.reward;
       if (a.reward_f64) a.reward_f64[off] = o.reward;
       if (a.discount) a.discount[off] = o.discount;
@@ -79,15 +80,11 @@ void host_run(const EnvParams& p, const LaunchArgs& a) {
 }
 
 // --------------------------- device dispatch --------------------------------
-// Graph-safe mode, large grids: advances the device clock after a transition launch (see the kernel's comment).
-static __global__ void advance_clock_kernel(unsigned long long* clock, unsigned long long steps) {
-  clock[0] += steps; clock[1] = 0ull; clock[2] = 0ull;
-}
-
 template <class F, int RK, bool kNoise, bool kTrack>
 int device_launch(bsb_env* e, LaunchArgs a, cudaStream_t stream) {
   const int K = e->p.obs_numel;
   const bool is_onehot = EmitKind<F>::value == EMIT_ONEHOT;
+  const bool is_image = EmitKind<F>::value == EMIT_IMAGE;
   const int64_t B = e->p.batch;
   a.emit_bulk = is_onehot ? e->deep_sea_bulk : e->emit_bulk;
   a.group_lanes = 1;
@@ -95,22 +92,29 @@ int device_launch(bsb_env* e, LaunchArgs a, cudaStream_t stream) {
   a.work_base = 0;
   a.lazy_fetch = e->lazy_fetch;
   a.l2_hint = e->l2_hint;
-  // Lanes per chunk.  The image emitter walks the chunk's lanes one 3 KB tile at a time, so it is bound by how many
-  // warps share the batch: keep >= 4 warps per SM by halving the chunk (down to 8 lanes) when 32-lane chunks would
-  // not.  Measured at 4 096 lanes (rollout us/step, 32-lane vs 8-lane chunks): mnist 14.8 -> 4.2; the deep_sea bulk
-  // path gets WORSE (N = 32: 2.4 -> 3.5, N = 50: 5.6 -> 6.0 -- fewer, larger TMA stores win), so it keeps 32.
+  // Row / board stages per warp: two (the next row block is rendered while the TMA unit still reads the previous
+  // one) unless that costs resident warps -- 16 warps per SM fit the register budget, so a warp can afford
+  // ~14 KB of shared memory.  umbrella_distract (103-float rows, 13 KB per stage) ran 7 warps per SM with two
+  // stages (profiles/r02a_family_ncu_metrics.csv) and is bound by integer-multiply latency, not by the store.
+  a.stage_rows = ((size_t)2 * 32 * (size_t)K * sizeof(float) <= 14 * 1024) ? 2 : 1;
+  a.cta_extra_floats = 0;
+  a.bad_action = e->bad_action_dev;
+  // Lanes per chunk.  The image emitter walks the chunk's lanes a few 3 KB tiles at a time, so it is bound by how
+  // many warps share the batch: keep >= 4 warps per SM by halving the chunk (down to 8 lanes) when 32-lane chunks
+  // would not.  Measured at 4 096 lanes (rollout us/step, 32-lane vs 8-lane chunks): mnist 14.8 -> 4.2; the deep_sea
+  // bulk path gets WORSE (N = 32: 2.4 -> 3.5, N = 50: 5.6 -> 6.0 -- fewer, larger TMA stores win), so it keeps 32.
   int chunk = 32;
-  if (EmitKind<F>::value == EMIT_IMAGE)
+  if (is_image)
     while (chunk > 8 && (B + chunk - 1) / chunk < 4 * (int64_t)e->num_sms) chunk >>= 1;
   if (e->chunk_lanes > 0) chunk = e->chunk_lanes;
   a.chunk_lanes = chunk;
   const int64_t n_chunks = (B + chunk - 1) / chunk;
   int threads = e->block_threads;
   bool persistent = false;
+  const size_t tile = (size_t)K * 4;
   if (is_onehot && a.emit_bulk) {
     // Lanes per bulk store: the largest power of two <= 16 with one store <= 40 KB (BSB_DEEP_SEA_GROUP overrides).
     // Measured on B200 (tools/bench_variants.py): N = 32 -> 8 lanes (32 KB stores), N = 50 -> 4 lanes (40 KB).
-    const size_t tile = (size_t)K * 4;
     int m = 1;
     while (m < 16 && (size_t)(2 * m) * tile <= 40 * 1024) m <<= 1;
     if (e->deep_sea_group > 0) m = e->deep_sea_group;
@@ -121,17 +125,35 @@ int device_launch(bsb_env* e, LaunchArgs a, cudaStream_t stream) {
       a.group_lanes = m; threads = 32; persistent = e->deep_sea_persistent != 0;
     }
   }
+  if (is_image && a.emit_bulk) {
+    // mnist through the TMA unit: groups of m <= 4 tiles staged in shared memory (two buffers per warp) plus m
+    // all-zero tiles per CTA for the LAST frames.  16-byte image loads need K % 16 == 0 (28 x 28 = 784 is).
+    int m = 4;
+    while (m > 1 && (size_t)TILE_STAGES * m * tile > 28 * 1024) m >>= 1;
+    if (m > chunk) m = chunk;
+    if ((K & 15) != 0 || (size_t)TILE_STAGES * m * tile > 64 * 1024) {
+      a.emit_bulk = 0;
+    } else {
+      a.group_lanes = m; threads = 64; a.cta_extra_floats = m * K; persistent = e->deep_sea_persistent != 0;
+    }
+  }
   a.use_pdl = (e->use_pdl && !a.no_pdl && a.mode == MODE_STEP && a.T == 1) ? 1 : 0;
-  const size_t per_warp = smem_floats_per_warp<F>(K, a.emit_bulk != 0, a.group_lanes) * sizeof(float);
-  size_t smem = per_warp * (size_t)(threads / 32);
-  while (smem > 96 * 1024 && threads > 32) { threads >>= 1; smem = per_warp * (size_t)(threads / 32); }
+  size_t per_warp = smem_floats_per_warp<F>(K, a.emit_bulk != 0, a.group_lanes, a.stage_rows) * sizeof(float);
+  if ((EmitKind<F>::value == EMIT_ROWS || EmitKind<F>::value == EMIT_TWOHOT) && per_warp > 96 * 1024) {
+    // rows / boards too long for a per-warp stage (catch boards beyond ~19 x 20 cells, umbrella_chain with more than
+    // ~380 distractors): boards fall back to shuffle-rendered vector stores, rows are rendered in place
+    a.emit_bulk = 0; a.stage_rows = 0; per_warp = 0;
+  }
+  const size_t cta_extra = (size_t)a.cta_extra_floats * sizeof(float);
+  size_t smem = per_warp * (size_t)(threads / 32) + cta_extra;
+  while (smem > 96 * 1024 && threads > 32) { threads >>= 1; smem = per_warp * (size_t)(threads / 32) + cta_extra; }
   if (smem > 200 * 1024) return fail(BSB_UNSUPPORTED, "observation too large for the staged emitter");
   auto kernel = transition_kernel<F, RK, kNoise, kTrack>;
   if (smem > 48 * 1024) BSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t grid = (n_chunks + threads / 32 - 1) / (threads / 32);
   if (persistent) {
     // As many CTAs as are co-resident (shared-memory bound; 1 KB per CTA is reserved by the driver); their warps
-    // draw 32-lane chunks from the environment's global counter.
+    // draw chunks from the environment's global counter.
     const int64_t per_sm = (int64_t)((227 * 1024) / (smem + 1024));
     const int64_t resident = (int64_t)e->num_sms * (per_sm < 1 ? 1 : (per_sm > 16 ? 16 : per_sm));
     if (grid > resident) {
@@ -142,7 +164,6 @@ int device_launch(bsb_env* e, LaunchArgs a, cudaStream_t stream) {
       persistent = false;      // everything is resident anyway: one chunk per warp
     }
   }
-  a.clock_external = (a.clock && grid > 2048) ? 1 : 0;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)grid);
@@ -157,11 +178,6 @@ int device_launch(bsb_env* e, LaunchArgs a, cudaStream_t stream) {
     cfg.numAttrs = 1;
   }
   BSB_CUDA(cudaLaunchKernelEx(&cfg, kernel, e->p, a));
-  if (a.clock_external) {
-    advance_clock_kernel<<<1, 1, 0, stream>>>(a.clock, a.mode == MODE_INIT ? 0ull : (unsigned long long)a.T);
-    BSB_CUDA(cudaGetLastError());
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-  }
   // chunks [warps, n_chunks) are fetched once each and every warp makes exactly one failing fetch
   // (graph-safe mode: the last CTA zeroes the counter instead)
   if (a.work_counter && !a.clock) e->work_base += (unsigned long long)n_chunks;

@@ -7,6 +7,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <chrono>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 #include "bsb_env.h"
 
@@ -173,7 +178,88 @@ void* mapped_device_pointer(bsb_env*, const void* host_ptr) {
   return nullptr;
 }
 
+
+// Host-supplied actions are validated before anything moves (the reference raises IndexError for an arm that does
+// not exist: bandit.py:61; catch.py:84).  Device-resident actions cannot be inspected without a synchronise: the
+// kernels clamp them and raise env->bad_action_host instead (bsb_invalid_actions).
+int check_host_actions(const bsb_env* e, const int32_t* actions, int64_t count) {
+  const uint32_t n = (uint32_t)e->p.num_actions;
+  for (int64_t k = 0; k < count; ++k)
+    if ((uint32_t)actions[k] >= n)
+      return fail(BSB_INVALID_ARGUMENT, "action " + std::to_string(actions[k]) + " at index " + std::to_string(k) +
+                                            " is outside [0, " + std::to_string(n) + ")");
+  return BSB_OK;
+}
+
+inline void cpu_relax() {
+#if defined(__x86_64__)
+  _mm_pause();
+#endif
+}
+
+// ---- host-driven steps: mailbox completion and pre-launched doorbell kernels --------------------------------
+int mailbox_open(bsb_env* e) {
+  if (e->mailbox) return BSB_OK;
+  void* host = nullptr; void* dev = nullptr;
+  BSB_CUDA(cudaHostAlloc(&host, sizeof(HostMailbox), cudaHostAllocMapped | cudaHostAllocPortable));
+  memset(host, 0, sizeof(HostMailbox));
+  BSB_CUDA(cudaHostGetDevicePointer(&dev, host, 0));
+  BSB_CUDA(cudaMalloc(reinterpret_cast<void**>(&e->mail), sizeof(DeviceMail)));
+  BSB_CUDA(cudaMemset(e->mail, 0, sizeof(DeviceMail)));
+  e->mailbox = static_cast<HostMailbox*>(host);
+  e->mailbox_dev = static_cast<HostMailbox*>(dev);
+  return BSB_OK;
+}
+
+// Enqueues one single-step launch that signals `ticket` through the mailbox.  wait_doorbell: the launch takes its
+// buffers from the mailbox once the host rings `ticket` (pre-launch); otherwise from `fields` right away.
+int mailbox_launch(bsb_env* e, unsigned long long ticket, int64_t step0, const MailFields* fields, bool wait_doorbell) {
+  LaunchArgs a;
+  memset(&a, 0, sizeof(a));
+  if (fields) {
+    a.actions = fields->actions; a.obs = fields->obs; a.reward = fields->reward; a.reward_f64 = fields->reward_f64;
+    a.discount = fields->discount; a.step_type = fields->step_type; a.obs_vec_ok = fields->obs_vec_ok;
+  }
+  a.T = 1; a.step0 = step0; a.mode = MODE_STEP;
+  a.mailbox = e->mailbox_dev; a.mail = e->mail; a.ticket = ticket; a.wait_doorbell = wait_doorbell ? 1 : 0;
+  a.doorbell_timeout_ns = e->doorbell_timeout_ns;
+  return run(e, a, e->copy_stream);
+}
+
+// Spins on the mailbox until `ticket` is done (the kernel's last CTA stores it after a system-scope fence).
+int mailbox_wait(bsb_env* e, unsigned long long ticket, bool* cancelled) {
+  const auto start = std::chrono::steady_clock::now();
+  unsigned long long seen;
+  uint32_t spins = 0;
+  while (((seen = e->mailbox->done) & ~MAIL_CANCEL) < ticket) {
+    cpu_relax();
+    if ((++spins & 0xfffffu) == 0 && std::chrono::steady_clock::now() - start > std::chrono::seconds(20)) {
+      cudaError_t err = cudaStreamSynchronize(e->copy_stream);      // a faulted kernel never signals: surface its error
+      if (err != cudaSuccess) return fail(BSB_CUDA_ERROR, std::string("host step: ") + cudaGetErrorString(err));
+      if ((e->mailbox->done & ~MAIL_CANCEL) >= ticket) { seen = e->mailbox->done; break; }
+      return fail(BSB_INTERNAL, "host step: the kernel finished without signalling the mailbox");
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  *cancelled = (seen & MAIL_CANCEL) != 0;
+  return BSB_OK;
+}
+
+// Stands down the pre-launched launch, if any: rings its ticket with the cancel bit and waits for it to leave.
+// Every entry point that enqueues work for this handle or reads its state calls this first.
+int flush_pending(bsb_env* e) {
+  if (!e || e->device < 0 || !e->pending_ticket) return BSB_OK;
+  DeviceGuard guard(e->device);
+  const unsigned long long ticket = e->pending_ticket;
+  e->pending_ticket = 0;
+  std::atomic_thread_fence(std::memory_order_release);
+  e->mailbox->doorbell = ticket | MAIL_CANCEL;
+  bool cancelled = false;
+  return mailbox_wait(e, ticket, &cancelled);
+}
+
 void destroy_env(bsb_env* e) {
+  flush_pending(e);
   DeviceGuard guard(e->device);
   for (size_t k = 0; k < e->allocs.size(); ++k) { if (e->device >= 0) cudaFree(e->allocs[k]); else free(e->allocs[k]); }
   if (e->device >= 0) {
@@ -182,6 +268,10 @@ void destroy_env(bsb_env* e) {
     if (e->d_reward64) cudaFree(e->d_reward64);
     if (e->d_obs) cudaFree(e->d_obs);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    if (e->order_event) cudaEventDestroy(e->order_event);
+    if (e->bad_action_host) cudaFreeHost(e->bad_action_host);
+    if (e->mailbox) cudaFreeHost(e->mailbox);
+    if (e->mail) cudaFree(e->mail);
   }
   delete e;
 }
@@ -229,6 +319,52 @@ __global__ void episode_sum_kernel(const EnvParams p, int64_t calls, const unsig
     double s = 0.0;
     for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(scratch + b * 5 + threadIdx.x);
     dst5[threadIdx.x] = s;
+  }
+  if (threadIdx.x == 0) *ticket = 0ull;
+}
+
+// The same reduction for up to kSumManyMax environments in ONE launch (blockIdx.y = environment): a log point of
+// the 23-experiment sweep is one kernel instead of 23.  Each environment keeps its own scratch and ticket, and
+// its sums are combined in block order, so the result equals episode_sum_kernel's bit for bit.
+constexpr int kSumManyMax = 64;
+struct SumJob { const double* ep; int64_t batch; int64_t calls; const unsigned long long* clock; double* scratch; };
+struct SumJobs { SumJob job[kSumManyMax]; };
+__global__ void episode_sum_many_kernel(const SumJobs jobs, double* dst) {
+  const SumJob j = jobs.job[blockIdx.y];
+  EnvParams p;
+  p.ep = const_cast<double*>(j.ep); p.batch = j.batch;
+  int64_t calls = j.calls;
+  if (j.clock) calls += (int64_t)*j.clock;
+  __shared__ double partial[5][kSumThreads / 32];
+  __shared__ bool is_last;
+  double v[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.batch; i += (int64_t)gridDim.x * blockDim.x)
+#pragma unroll
+    for (int f = 0; f < 5; ++f) v[f] += episode_stat(p, i, f, calls);
+#pragma unroll
+  for (int f = 0; f < 5; ++f)
+    for (int o = 16; o > 0; o >>= 1) v[f] += __shfl_down_sync(0xffffffffu, v[f], o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) for (int f = 0; f < 5; ++f) partial[f][warp] = v[f];
+  __syncthreads();
+  // blocks that own no lanes of this environment contribute exact zeros, so the block-order sum below equals the
+  // one episode_sum_kernel forms over min(blocks, ceil(batch / threads)) blocks
+  if (threadIdx.x < 5) {
+    double s = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += partial[threadIdx.x][w];
+    j.scratch[blockIdx.x * 5 + threadIdx.x] = s;
+    __threadfence();
+  }
+  __syncthreads();
+  unsigned long long* ticket = reinterpret_cast<unsigned long long*>(j.scratch + kSumBlocks * 5);
+  if (threadIdx.x == 0) is_last = atomicAdd(ticket, 1ull) == (unsigned long long)gridDim.x - 1ull;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (threadIdx.x < 5) {
+    double s = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(j.scratch + b * 5 + threadIdx.x);
+    dst[blockIdx.y * 5 + threadIdx.x] = s;
   }
   if (threadIdx.x == 0) *ticket = 0ull;
 }
@@ -282,6 +418,10 @@ int32_t bsb_create(const bsb_config* config, int64_t batch, int32_t device, uint
     e->num_sms = 148;
     if (device >= 0) { int n = 0; if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && n > 0) e->num_sms = n; }
   }
+  e->order_event = nullptr; e->bad_action_host = nullptr; e->bad_action_dev = nullptr;
+  e->mailbox = nullptr; e->mailbox_dev = nullptr; e->mail = nullptr; e->next_ticket = 0; e->pending_ticket = 0;
+  { const char* v = getenv("BSB_DOORBELL_TIMEOUT_MS"); const long ms = v ? atol(v) : 200; e->doorbell_timeout_ns = (unsigned long long)(ms > 0 ? ms : 200) * 1000000ull; }
+  { const char* v = getenv("BSB_HOST_SPIN"); e->host_spin = v ? (atoi(v) != 0) : 1; }
   e->h2d_actions = nullptr; e->d_reward = nullptr; e->d_reward64 = nullptr; e->d_discount = nullptr; e->d_step_type = nullptr; e->d_obs = nullptr;
   e->copy_stream = nullptr;
   DeviceGuard guard(device);
@@ -329,7 +469,18 @@ int32_t bsb_create(const bsb_config* config, int64_t batch, int32_t device, uint
     BSB_TRY(env_upload(e, l, c.table2, (size_t)c.table2_bytes));
     p.images = d; p.labels = l;
   }
-  if (device >= 0) { BSB_TRY(env_alloc_t(e, &e->work_counter, 1, false)); BSB_TRY(env_alloc_t(e, &e->clock, 4, false)); BSB_TRY(env_alloc_t(e, &e->sum_scratch, kSumBlocks * 5 + 1, false)); }
+  if (device >= 0) {
+    BSB_TRY(env_alloc_t(e, &e->work_counter, 1, false));
+    BSB_TRY(env_alloc_t(e, &e->clock, CLOCK_WORDS, false));
+    BSB_TRY(env_alloc_t(e, &e->sum_scratch, kSumBlocks * 5 + 1, false));
+    void* flag = nullptr; void* flag_dev = nullptr;
+    if (cudaHostAlloc(&flag, sizeof(int32_t), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess ||
+        cudaHostGetDevicePointer(&flag_dev, flag, 0) != cudaSuccess) {
+      destroy_env(e); return fail(BSB_OUT_OF_MEMORY, "pinned allocation for the invalid-action flag failed");
+    }
+    e->bad_action_host = static_cast<int32_t*>(flag); *e->bad_action_host = 0;
+    e->bad_action_dev = static_cast<int32_t*>(flag_dev);
+  }
   // lane state
   BSB_TRY(env_alloc_t(e, &p.st_word, B, true));
   if (c.family == BSB_MEMORY_CHAIN) BSB_TRY(env_alloc_t(e, &p.st_ctx, B, true));
@@ -410,11 +561,12 @@ static void advance_steps(bsb_env* env, int64_t n) { if (!env->graph_safe) env->
 
 int32_t bsb_steps_done(const bsb_env* env, int64_t* steps) {
   if (!env || !steps) return fail(BSB_INVALID_ARGUMENT, "null argument");
-  return current_steps(env, steps);
+  return current_steps(env, steps);       // a pre-launched host step (if any) has not been counted: it is for step steps_done
 }
 
 int32_t bsb_reset(bsb_env* env, const bsb_outputs* out, void* stream) {
   if (!env || !out || !out->observation) return fail(BSB_INVALID_ARGUMENT, "bsb_reset needs outputs with an observation buffer");
+  { int frc = flush_pending(env); if (frc != BSB_OK) return frc; }
   LaunchArgs a = make_args(env, out, nullptr, 1, MODE_RESET);
   int rc = run(env, a, static_cast<cudaStream_t>(stream));
   if (rc == BSB_OK) advance_steps(env, 1);
@@ -423,6 +575,8 @@ int32_t bsb_reset(bsb_env* env, const bsb_outputs* out, void* stream) {
 
 int32_t bsb_step(bsb_env* env, const int32_t* actions, const bsb_outputs* out, void* stream) {
   if (!env || !actions || !out || !out->observation) return fail(BSB_INVALID_ARGUMENT, "bsb_step needs actions and outputs with an observation buffer");
+  { int frc = flush_pending(env); if (frc != BSB_OK) return frc; }
+  if (env->device < 0) { int vrc = check_host_actions(env, actions, env->p.batch); if (vrc != BSB_OK) return vrc; }
   LaunchArgs a = make_args(env, out, actions, 1, MODE_STEP);
   int rc = run(env, a, static_cast<cudaStream_t>(stream));
   if (rc == BSB_OK) advance_steps(env, 1);
@@ -433,6 +587,8 @@ int32_t bsb_rollout(bsb_env* env, int64_t num_steps, const int32_t* actions, uin
                     const bsb_outputs* out, int32_t* actions_out, void* stream) {
   if (!env || !out || !out->observation) return fail(BSB_INVALID_ARGUMENT, "bsb_rollout needs outputs with an observation buffer");
   if (num_steps <= 0) return fail(BSB_INVALID_ARGUMENT, "num_steps must be positive");
+  { int frc = flush_pending(env); if (frc != BSB_OK) return frc; }
+  if (env->device < 0 && actions) { int vrc = check_host_actions(env, actions, num_steps * env->p.batch); if (vrc != BSB_OK) return vrc; }
   LaunchArgs a = make_args(env, out, actions, num_steps, MODE_STEP);
   a.action_seed = action_seed; a.actions_out = actions_out;
   int rc = run(env, a, static_cast<cudaStream_t>(stream));
@@ -472,6 +628,7 @@ static int copy_field(bsb_env* env, const double* src, double* dst, void* stream
 int32_t bsb_read_info(bsb_env* env, int32_t index, double* dst, void* stream) {
   if (!env || !dst) return fail(BSB_INVALID_ARGUMENT, "null argument");
   if (index < 0 || index >= env->names.n) return fail(BSB_INVALID_ARGUMENT, "info index out of range");
+  { int frc = flush_pending(env); if (frc != BSB_OK) return frc; }
   return copy_field(env, env->p.info + (size_t)index * (size_t)env->p.batch, dst, stream);
 }
 
@@ -479,6 +636,7 @@ int32_t bsb_read_episode_stats(bsb_env* env, int32_t field, double* dst, void* s
   if (!env || !dst) return fail(BSB_INVALID_ARGUMENT, "null argument");
   if (!env->p.ep) return fail(BSB_INVALID_ARGUMENT, "environment was created without BSB_FLAG_TRACK_EPISODES");
   if (field < 0 || field >= 5) return fail(BSB_INVALID_ARGUMENT, "episode-stat field out of range");
+  { int frc = flush_pending(env); if (frc != BSB_OK) return frc; }
   const int64_t B = env->p.batch;
   if (env->device >= 0) {
     DeviceGuard guard(env->device);
@@ -494,6 +652,7 @@ int32_t bsb_read_episode_stats(bsb_env* env, int32_t field, double* dst, void* s
 int32_t bsb_sum_episode_stats(bsb_env* env, double* dst5, void* stream) {
   if (!env || !dst5) return fail(BSB_INVALID_ARGUMENT, "null argument");
   if (!env->p.ep) return fail(BSB_INVALID_ARGUMENT, "environment was created without BSB_FLAG_TRACK_EPISODES");
+  { int frc = flush_pending(env); if (frc != BSB_OK) return frc; }
   const int64_t B = env->p.batch;
   if (env->device >= 0) {
     DeviceGuard guard(env->device);
@@ -514,6 +673,31 @@ int32_t bsb_sum_episode_stats(bsb_env* env, double* dst5, void* stream) {
   return BSB_OK;
 }
 
+int32_t bsb_sum_episode_stats_many(bsb_env* const* envs, int32_t count, double* dst, void* stream) {
+  if (!envs || !dst || count <= 0) return fail(BSB_INVALID_ARGUMENT, "bad arguments");
+  for (int32_t k = 0; k < count; ++k) {
+    if (!envs[k]) return fail(BSB_INVALID_ARGUMENT, "null environment");
+    if (!envs[k]->p.ep) return fail(BSB_INVALID_ARGUMENT, "environment was created without BSB_FLAG_TRACK_EPISODES");
+    if (envs[k]->device != envs[0]->device) return fail(BSB_INVALID_ARGUMENT, "environments live on different devices");
+  }
+  if (envs[0]->device < 0 || count > kSumManyMax) {       // host path / oversized lists: one environment at a time
+    for (int32_t k = 0; k < count; ++k) { int rc = bsb_sum_episode_stats(envs[k], dst + 5 * k, stream); if (rc != BSB_OK) return rc; }
+    return BSB_OK;
+  }
+  DeviceGuard guard(envs[0]->device);
+  SumJobs jobs;
+  memset(&jobs, 0, sizeof(jobs));
+  for (int32_t k = 0; k < count; ++k) {
+    { int frc = flush_pending(envs[k]); if (frc != BSB_OK) return frc; }
+    jobs.job[k].ep = envs[k]->p.ep; jobs.job[k].batch = envs[k]->p.batch; jobs.job[k].calls = envs[k]->steps_done;
+    jobs.job[k].clock = envs[k]->graph_safe ? envs[k]->clock : nullptr; jobs.job[k].scratch = envs[k]->sum_scratch;
+  }
+  episode_sum_many_kernel<<<dim3(kSumBlocks, (unsigned)count), kSumThreads, 0, static_cast<cudaStream_t>(stream)>>>(jobs, dst);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  BSB_CUDA(cudaGetLastError());
+  return BSB_OK;
+}
+
 int32_t bsb_state_bytes(const bsb_env* env, int64_t* nbytes) {
   if (!env || !nbytes) return fail(BSB_INVALID_ARGUMENT, "null argument");
   size_t total = sizeof(int64_t);
@@ -526,6 +710,7 @@ int32_t bsb_get_state(bsb_env* env, void* dst_host, int64_t nbytes, void* stream
   if (!env || !dst_host) return fail(BSB_INVALID_ARGUMENT, "null argument");
   bsb_state_bytes(env, &need);
   if (nbytes != need) return fail(BSB_INVALID_ARGUMENT, "state buffer has the wrong size");
+  { int frc = flush_pending(env); if (frc != BSB_OK) return frc; }
   DeviceGuard guard(env->device);
   char* dst = static_cast<char*>(dst_host);
   if (env->device >= 0) BSB_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
@@ -545,6 +730,7 @@ int32_t bsb_set_state(bsb_env* env, const void* src_host, int64_t nbytes, void* 
   if (!env || !src_host) return fail(BSB_INVALID_ARGUMENT, "null argument");
   bsb_state_bytes(env, &need);
   if (nbytes != need) return fail(BSB_INVALID_ARGUMENT, "state buffer has the wrong size");
+  { int frc = flush_pending(env); if (frc != BSB_OK) return frc; }
   DeviceGuard guard(env->device);
   const char* src = static_cast<const char*>(src_host);
   if (env->device >= 0) BSB_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
@@ -567,7 +753,30 @@ int32_t bsb_set_state(bsb_env* env, const void* src_host, int64_t nbytes, void* 
   return BSB_OK;
 }
 
-int32_t bsb_step_host(bsb_env* env, const int32_t* actions, const bsb_outputs* host_out, float* device_obs) {
+int32_t bsb_invalid_actions(bsb_env* env, int32_t* seen) {
+  if (!env || !seen) return fail(BSB_INVALID_ARGUMENT, "null argument");
+  *seen = 0;
+  if (env->bad_action_host) { *seen = *env->bad_action_host; *env->bad_action_host = 0; }
+  return BSB_OK;
+}
+
+int32_t bsb_host_flush(bsb_env* env) {
+  if (!env) return fail(BSB_INVALID_ARGUMENT, "null argument");
+  return flush_pending(env);
+}
+
+// Reports (and clears) an out-of-range action seen by the kernels of a synchronous host step.
+static int report_bad_actions(bsb_env* env) {
+  if (env->bad_action_host && *env->bad_action_host) {
+    *env->bad_action_host = 0;
+    return fail(BSB_INVALID_ARGUMENT, "an action was outside [0, " + std::to_string(env->p.num_actions) +
+                                          "): the step was taken with that action clamped into range");
+  }
+  return BSB_OK;
+}
+
+int32_t bsb_step_host(bsb_env* env, const int32_t* actions, const bsb_outputs* host_out, float* device_obs,
+                      void* caller_stream, uint32_t flags) {
   if (!env || !actions || !host_out) return fail(BSB_INVALID_ARGUMENT, "null argument");
   if (env->device < 0) {
     if (!host_out->observation) return fail(BSB_INVALID_ARGUMENT, "a host environment writes observations to host_out->observation");
@@ -577,6 +786,14 @@ int32_t bsb_step_host(bsb_env* env, const int32_t* actions, const bsb_outputs* h
   DeviceGuard guard(env->device);
   const size_t B = (size_t)env->p.batch, K = (size_t)env->p.obs_numel;
   if (!env->copy_stream) BSB_CUDA(cudaStreamCreateWithFlags(&env->copy_stream, cudaStreamNonBlocking));
+  if (flags & BSB_HOST_ORDER_AFTER_STREAM) {
+    // Work the caller enqueued earlier on ITS stream (bsb_reset / bsb_step / bsb_rollout of this handle) must have
+    // finished with the lane state before this step touches it: fence the handle's stream behind it.
+    { int frc = flush_pending(env); if (frc != BSB_OK) return frc; }
+    if (!env->order_event) BSB_CUDA(cudaEventCreateWithFlags(&env->order_event, cudaEventDisableTiming));
+    BSB_CUDA(cudaEventRecord(env->order_event, static_cast<cudaStream_t>(caller_stream)));
+    BSB_CUDA(cudaStreamWaitEvent(env->copy_stream, env->order_event, 0));
+  }
 
   // Zero-copy path: when the caller's action and scalar buffers are PINNED host memory (device-addressable under
   // unified addressing), the transition kernel reads the actions from and writes reward / discount / step_type to
@@ -600,20 +817,67 @@ int32_t bsb_step_host(bsb_env* env, const int32_t* actions, const bsb_outputs* h
                             (!host_out->discount || d_discount) && (!host_out->step_type || d_step_type);
     if (all_mapped) {
       if (!device_obs && !env->d_obs) BSB_CUDA(cudaMalloc(&env->d_obs, B * K * 4));
-      bsb_outputs dev;
-      dev.observation = device_obs ? device_obs : env->d_obs;
-      dev.reward = static_cast<float*>(d_reward);
-      dev.reward_f64 = static_cast<double*>(d_reward64);
-      dev.discount = static_cast<float*>(d_discount);
-      dev.step_type = static_cast<int32_t*>(d_step_type);
+      MailFields f;
+      memset(&f, 0, sizeof(f));
+      f.actions = static_cast<const int32_t*>(d_actions);
+      f.obs = device_obs ? device_obs : env->d_obs;
+      f.reward = static_cast<float*>(d_reward);
+      f.reward_f64 = static_cast<double*>(d_reward64);
+      f.discount = static_cast<float*>(d_discount);
+      f.step_type = static_cast<int32_t*>(d_step_type);
+      f.obs_vec_ok = (reinterpret_cast<uintptr_t>(f.obs) % 16 == 0) ? 1 : 0;
       cudaStream_t zs = env->copy_stream;
-      int zrc = bsb_step(env, static_cast<const int32_t*>(d_actions), &dev, zs);
-      if (zrc != BSB_OK) return zrc;
-      if (host_out->observation) BSB_CUDA(cudaMemcpyAsync(host_out->observation, dev.observation, B * K * 4, cudaMemcpyDeviceToHost, zs));
-      BSB_CUDA(cudaStreamSynchronize(zs));
-      return BSB_OK;
+      // Completion through the mailbox (BSB_HOST_SPIN=0 turns it off): the kernel's last CTA stores the ticket into
+      // pinned host memory after a system-scope fence and the host spins on that word -- a stream synchronise costs
+      // a wake-up of ~10 us per step.  Observations copied to the host, graph-safe handles and unaligned
+      // observation buffers keep the synchronise.
+      const bool spin = env->host_spin && !env->graph_safe && !host_out->observation && f.obs_vec_ok;
+      if (!spin) {
+        { int frc = flush_pending(env); if (frc != BSB_OK) return frc; }
+        bsb_outputs dev;
+        dev.observation = f.obs; dev.reward = f.reward; dev.reward_f64 = f.reward_f64; dev.discount = f.discount; dev.step_type = f.step_type;
+        int zrc = bsb_step(env, f.actions, &dev, zs);
+        if (zrc != BSB_OK) return zrc;
+        if (host_out->observation) BSB_CUDA(cudaMemcpyAsync(host_out->observation, dev.observation, B * K * 4, cudaMemcpyDeviceToHost, zs));
+        BSB_CUDA(cudaStreamSynchronize(zs));
+        return report_bad_actions(env);
+      }
+      { int mrc = mailbox_open(env); if (mrc != BSB_OK) return mrc; }
+      const bool prelaunch = (flags & BSB_HOST_PRELAUNCH) != 0;
+      for (int attempt = 0; attempt < 2; ++attempt) {
+        unsigned long long ticket;
+        if (env->pending_ticket) {
+          // The kernel of this step is already resident and polling: hand it the buffers and ring.
+          ticket = env->pending_ticket;
+          env->pending_ticket = 0;
+          env->mailbox->in = f;
+          std::atomic_thread_fence(std::memory_order_release);
+          env->mailbox->doorbell = ticket;
+        } else {
+          ticket = ++env->next_ticket;
+          int lrc = mailbox_launch(env, ticket, env->steps_done, &f, false);
+          if (lrc != BSB_OK) return lrc;
+        }
+        if (prelaunch) {
+          // Queue the NEXT step's kernel now: it becomes resident as this one drains and waits for its doorbell,
+          // so the next call pays neither a launch nor a wake-up.  It stands down by itself after
+          // BSB_DOORBELL_TIMEOUT_MS without a ring.
+          const unsigned long long next = ++env->next_ticket;
+          int lrc = mailbox_launch(env, next, env->steps_done + 1, nullptr, true);
+          if (lrc != BSB_OK) return lrc;
+          env->pending_ticket = next;
+        }
+        bool cancelled = false;
+        { int wrc = mailbox_wait(env, ticket, &cancelled); if (wrc != BSB_OK) return wrc; }
+        if (!cancelled) { env->steps_done += 1; return report_bad_actions(env); }
+        // The pre-launched kernel had given up waiting before the ring arrived: nothing was stepped.  The launch
+        // queued behind it carries the wrong step index now; stand it down and take the step again, launched now.
+        { int frc = flush_pending(env); if (frc != BSB_OK) return frc; }
+      }
+      return fail(BSB_INTERNAL, "host step: a freshly launched kernel reported a cancelled doorbell");
     }
   }
+  { int frc = flush_pending(env); if (frc != BSB_OK) return frc; }
   if (!env->h2d_actions) BSB_CUDA(cudaMalloc(&env->h2d_actions, B * 4));
   // reward | discount | step_type live in ONE device block so that a caller who keeps its three host arrays
   // back to back (BatchedEnvironment.make_host_buffers does) gets them with a single D2H copy.
@@ -624,6 +888,7 @@ int32_t bsb_step_host(bsb_env* env, const int32_t* actions, const bsb_outputs* h
   }
   if (host_out->reward_f64 && !env->d_reward64) BSB_CUDA(cudaMalloc(&env->d_reward64, B * 8));
   if (!device_obs && !env->d_obs) BSB_CUDA(cudaMalloc(&env->d_obs, B * K * 4));
+  { int vrc = check_host_actions(env, actions, (int64_t)B); if (vrc != BSB_OK) return vrc; }
   cudaStream_t s = env->copy_stream;
   BSB_CUDA(cudaMemcpyAsync(env->h2d_actions, actions, B * 4, cudaMemcpyHostToDevice, s));
   bsb_outputs dev;

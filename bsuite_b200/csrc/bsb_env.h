@@ -58,6 +58,18 @@ struct bsb_env {
   // bsb_step_host scratch (device)
   int32_t* h2d_actions; float* d_reward; double* d_reward64; float* d_discount; int32_t* d_step_type; float* d_obs;
   cudaStream_t copy_stream;
+  cudaEvent_t order_event;            // BSB_HOST_ORDER_AFTER_STREAM: fences copy_stream behind the caller's stream
+  // Out-of-range actions: the kernels clamp them before any table index or state packing and raise
+  // this pinned flag; bsb_step_host / bsb_invalid_actions report it.
+  int32_t* bad_action_host; int32_t* bad_action_dev;
+  // Host-driven steps without a stream synchronise (bsb_step_host on pinned buffers): the kernel signals completion
+  // through a pinned mailbox the host spins on; with BSB_HOST_PRELAUNCH the next step's kernel is already queued
+  // and waits for the mailbox doorbell (bsb_kernels.cuh, HostMailbox).
+  bsb::HostMailbox* mailbox; bsb::HostMailbox* mailbox_dev; bsb::DeviceMail* mail;
+  unsigned long long next_ticket;     // last ticket handed out
+  unsigned long long pending_ticket;  // pre-launched launch waiting for its doorbell (0 = none); it is for step steps_done
+  unsigned long long doorbell_timeout_ns;
+  int host_spin;                      // BSB_HOST_SPIN (default 1): completion through the mailbox instead of a synchronise
 };
 
 namespace bsb {

@@ -537,21 +537,24 @@ struct Mnist {
 // values that change at episode boundaries only, because all lanes step in lock-step:
 //   ep[0] total_return     dense      ep[1] episode         += 1 at LAST
 //   ep[2] episode_return   dense      ep[3] first_count     += 1 at FIRST
-//                                     ep[4] start_call      = global call index of the latest FIRST
+//                                     ep[4] start_call      = global call index of the FIRST that followed the
+//                                                             latest LAST, + 1 per further FIRST since
 //   steps       = calls - first_count              (every call that did not return FIRST is a transition)
-//   episode_len = calls - 1 - start_call           (transitions since the latest FIRST; 0 before any)
-// The reference zeroes episode_len / episode_return right after logging a LAST timestep; here they restart at the
-// NEXT episode's FIRST, so from a LAST timestep -- the moment the reference writes its row (:99-101) -- until the
-// lane steps again they hold the finished episode's values.
+//   episode_len = calls - 1 - start_call           (transitions since the latest LAST; 0 before any call)
+// The reference zeroes episode_len / episode_return right after logging a LAST timestep (:105-107) and NOT at a
+// FIRST: an explicit reset() in the middle of an episode leaves both running.  Here they restart at the first
+// call after a LAST (`after_last`: the lane's _reset_next_step flag before the call), so from a LAST timestep --
+// the moment the reference writes its row (:99-101) -- until the lane steps again they hold the finished episode's
+// values, and a mid-episode reset() only discounts its own non-transition call.
 struct EpisodeStats {
   double total_return, episode_return;
   BSB_HD void load(const EnvParams& p, int64_t i) { total_return = p.ep[i]; episode_return = p.ep[2 * p.batch + i]; }
   BSB_HD void store(const EnvParams& p, int64_t i) const { p.ep[i] = total_return; p.ep[2 * p.batch + i] = episode_return; }
-  BSB_HD void track(const EnvParams& p, int64_t i, const StepOut& o, int64_t call_index) {
+  BSB_HD void track(const EnvParams& p, int64_t i, const StepOut& o, int64_t call_index, bool after_last) {
     if (o.step_type == FIRST) {
-      episode_return = 0.0;
       p.ep[3 * p.batch + i] += 1.0;
-      p.ep[4 * p.batch + i] = (double)call_index;
+      if (after_last) { episode_return = 0.0; p.ep[4 * p.batch + i] = (double)call_index; }
+      else p.ep[4 * p.batch + i] += 1.0;
       return;
     }
     episode_return += o.reward; total_return += o.reward;

@@ -58,8 +58,41 @@ struct LaunchArgs {
   // Null in the default mode, where `step0` / `work_base` arrive as launch arguments from the host's counters.
   unsigned long long* clock;
   int32_t no_pdl;           // set while the stream is being captured
-  int32_t clock_external;   // graph-safe mode, large grids: a one-thread kernel enqueued after this one advances the clock
   int32_t chunk_lanes;      // lanes per chunk (= per warp pass): 32, or 16 / 8 when the batch would under-fill the SMs
+  int32_t stage_rows;       // row / board emitters: number of [32, K] shared-memory stages per warp (2: double buffered;
+                            // 1: long rows, where a second stage would cost resident warps; 0: straight to global memory)
+  int32_t cta_extra_floats; // shared memory after the per-warp stages (mnist bulk path: the CTA's all-zero tiles)
+  // Host-driven steps (bsb_step_host, pinned buffers): completion is signalled through a pinned mailbox; with
+  // BSB_HOST_PRELAUNCH the launch is even enqueued BEFORE its inputs exist and waits for the host to ring
+  // `ticket`, taking pointers and actions from the mailbox.
+  struct HostMailbox* mailbox;       // pinned host memory, device alias (null: ordinary launch).  The last CTA to
+                                     // finish stores `done = ticket` there: the host spins on it instead of
+                                     // paying a stream synchronise.
+  struct DeviceMail* mail;           // device memory: doorbell relay + finished-CTA counter
+  unsigned long long ticket;
+  int32_t wait_doorbell;             // 1: pre-launched -- poll the doorbell for `ticket`, then take the buffers from the mailbox
+  unsigned long long doorbell_timeout_ns;
+  int32_t* bad_action;      // pinned host flag (device alias): set to 1 when an action is outside [0, num_actions)
+};
+
+// Host <-> device mailbox of the doorbell mode.  The host fills `in` and then stores `doorbell = ticket` (release
+// order); block 0 of the waiting launch polls it over PCIe, copies `in` to device memory and relays the ticket to the
+// other blocks through L2.  The last block to finish stores `done = ticket` after a system-scope fence, so every
+// output written to host memory (reward / discount / step_type, zero-copy) is visible when the host sees it.
+static const unsigned long long MAIL_CANCEL = 1ull << 63;      // doorbell: skip the step; done: the step was skipped
+struct MailFields {
+  const int32_t* actions; float* obs; float* reward; double* reward_f64; float* discount; int32_t* step_type;
+  int32_t obs_vec_ok, pad;
+};
+struct HostMailbox {
+  volatile unsigned long long doorbell; unsigned long long pad0[7];     // own 64-byte line
+  MailFields in;                          unsigned long long pad1[1];
+  volatile unsigned long long done;     unsigned long long pad2[7];
+};
+struct DeviceMail {
+  volatile unsigned long long relay;      // ticket (| MAIL_CANCEL) most recently taken from the host doorbell
+  unsigned long long finished;            // blocks of the current launch that have finished
+  MailFields in;                          // the host's fields, copied once per launch by block 0
 };
 
 enum { MODE_STEP = 0, MODE_RESET = 1, MODE_INIT = 2 };
@@ -123,7 +156,7 @@ template <class F> struct EmitKind { static const int value = EMIT_ROWS; };
 template <> struct EmitKind<DeepSea> { static const int value = EMIT_ONEHOT; };
 template <> struct EmitKind<Catch> { static const int value = EMIT_TWOHOT; };
 template <> struct EmitKind<Mnist> { static const int value = EMIT_IMAGE; };
-static const int ROW_STAGES = 2;      // double-buffered [32, K] stage per warp
+static const int ROW_STAGES = 2;      // at most: double-buffered [32, K] stage per warp (LaunchArgs::stage_rows)
 static const int TILE_STAGES = 2;     // deep_sea bulk path: double-buffered groups of `group_lanes` tiles per warp
 
 // Dynamic shared memory per warp, in floats.
@@ -131,10 +164,11 @@ template <class F> inline
 #if defined(__CUDACC__)
 __host__ __device__
 #endif
-size_t smem_floats_per_warp(int K, bool emit_bulk, int group_lanes) {
-  if (EmitKind<F>::value == EMIT_ROWS || EmitKind<F>::value == EMIT_TWOHOT) return (size_t)ROW_STAGES * 32 * (size_t)K;
+size_t smem_floats_per_warp(int K, bool emit_bulk, int group_lanes, int row_stages) {
+  if (EmitKind<F>::value == EMIT_ROWS || EmitKind<F>::value == EMIT_TWOHOT) return (size_t)row_stages * 32 * (size_t)K;
   if (EmitKind<F>::value == EMIT_ONEHOT && emit_bulk) return (size_t)TILE_STAGES * (size_t)group_lanes * (size_t)K;
-  if (EmitKind<F>::value == EMIT_IMAGE) return 256;        // int8 pixel -> float32 lookup table
+  if (EmitKind<F>::value == EMIT_IMAGE)                    // int8 pixel -> float32 table (+ two staging buffers of m tiles)
+    return 256 + (emit_bulk ? (size_t)TILE_STAGES * (size_t)group_lanes * (size_t)K : 0);
   return 0;
 }
 
@@ -271,6 +305,82 @@ __device__ __forceinline__ void emit_image(const EnvParams& p, const float* lut,
   }
 }
 
+// image.astype(float32) / 255 (mnist.py:64) without a table or an IEEE division: q0 = v * rcp, one Newton
+// residual step with two FMAs.  With rcp the correctly rounded 1/255 this is the correctly rounded quotient for
+// every int8 v (Markstein's theorem; all 256 inputs are checked against Mnist::pixel in tests/test_golden_parity.py
+// and by `static` reasoning: |v| <= 128 is exact in float32 and no intermediate over- or underflows).  The table
+// of emit_image costs one LDS per pixel but serialises on bank conflicts when neighbouring pixels differ.
+__device__ __forceinline__ float pixel_div255(int v) {
+  const float x = (float)v, rcp = 1.0f / 255.0f;      // constant-folded by the compiler
+  const float q = __fmul_rn(x, rcp);
+  const float r = __fmaf_rn(-255.0f, q, x);
+  return __fmaf_rn(r, rcp, q);
+}
+__device__ __forceinline__ float4 pixels4(uint32_t w) {
+  return make_float4(pixel_div255((int)(int8_t)(w & 0xffu)), pixel_div255((int)(int8_t)((w >> 8) & 0xffu)),
+                     pixel_div255((int)(int8_t)((w >> 16) & 0xffu)), pixel_div255((int)(int8_t)(w >> 24)));
+}
+
+// Image tiles through shared memory and the TMA unit (K % 16 == 0, e.g. 28 x 28).  Lanes are taken in groups of
+// `m` (<= 4) consecutive lanes = m contiguous tiles in global memory:
+//   * a group whose lanes all show the all-zero LAST frame (mnist.py:74; every other step of every lane) is ONE
+//     bulk store from the CTA's zero tiles -- nothing is staged, nothing is waited for;
+//   * otherwise all 16-byte loads of the group's int8 images (49 per 28 x 28 tile, <= 8 per thread) are issued
+//     before the first conversion, the float32 tiles land in one of two staging buffers and leave as one bulk
+//     store of m * 4K bytes.
+// stage = [256 floats: table of the vector path][2 x m x K floats]; `emitted` counts staged stores (buffer parity).
+__device__ __forceinline__ void emit_image_bulk(const EnvParams& p, float* stage, const float* cta_zero, float* obs_t,
+                                                int64_t warp_base, int n_lanes, int K, int image, int m, int l2_hint,
+                                                unsigned& emitted) {
+  constexpr int MAXM = 4;
+  const int tid = threadIdx.x & 31;
+  float* tiles = stage + 256;
+  const int K16 = K >> 4;
+  const unsigned showing = __ballot_sync(0xffffffffu, image >= 0);
+  for (int g0 = 0; g0 < n_lanes; g0 += m) {
+    const int in_group = (n_lanes - g0) < m ? (n_lanes - g0) : m;
+    float* dst = obs_t + (warp_base + g0) * (int64_t)K;
+    const uint32_t bytes = (uint32_t)in_group * (uint32_t)K * 4u;
+    if (((showing >> g0) & ((1u << in_group) - 1u)) == 0u) {
+      if (tid == 0) { bulk_store_obs(dst, cta_zero, bytes, l2_hint); bulk_commit(); }
+      continue;
+    }
+    float* buf = tiles + (size_t)(emitted & 1u) * m * K;
+    if (tid == 0) bulk_wait_read<1>();      // at most the newest store is still reading: never this buffer
+    __syncwarp();
+    int img[MAXM];
+#pragma unroll
+    for (int j = 0; j < MAXM; ++j) img[j] = __shfl_sync(0xffffffffu, image, (g0 + j) & 31);
+    for (int q0 = 0; q0 < K16; q0 += 64) {
+      uint4 c[MAXM][2];
+#pragma unroll
+      for (int j = 0; j < MAXM; ++j)
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int q = q0 + r * 32 + tid;
+          c[j][r] = make_uint4(0u, 0u, 0u, 0u);
+          if (j < in_group && img[j] >= 0 && q < K16)
+            c[j][r] = __ldg(reinterpret_cast<const uint4*>(p.images + (int64_t)img[j] * K) + q);
+        }
+#pragma unroll
+      for (int j = 0; j < MAXM; ++j)
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int q = q0 + r * 32 + tid;
+          if (j < in_group && q < K16) {
+            float4* out = reinterpret_cast<float4*>(buf + (size_t)j * K) + 4 * q;
+            out[0] = pixels4(c[j][r].x); out[1] = pixels4(c[j][r].y);
+            out[2] = pixels4(c[j][r].z); out[3] = pixels4(c[j][r].w);
+          }
+        }
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (tid == 0) { bulk_store_obs(dst, buf, bytes, l2_hint); bulk_commit(); }
+    ++emitted;
+  }
+}
+
 // Stream the warp's staged [n_lanes, K] block with ordinary stores (ragged tail warps, unaligned buffers).
 __device__ __forceinline__ void flush_rows_vec(const float* stage, float* obs_t, int64_t warp_base, int n_lanes, int K, bool vec) {
   const int tid = threadIdx.x & 31;
@@ -349,17 +459,39 @@ template <> struct MinBlocksPerSM<DiscountingChain> { static const int value = 8
 #else
 #define BSB_LAUNCH_MIN_BLOCKS(F) MinBlocksPerSM<F>::value
 #endif
+// System-scope accesses to the pinned mailbox (host memory over PCIe) and volatile accesses to its L2 relay.
+__device__ __forceinline__ unsigned long long ld_sys_u64(const volatile unsigned long long* ptr) {
+  unsigned long long v; asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(ptr) : "memory"); return v;
+}
+__device__ __forceinline__ void st_sys_u64(volatile unsigned long long* ptr, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(ptr), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t;
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// Graph-safe mode keeps {steps, chunk counter, finished groups} in clock[0..2]; the finished-CTA count is split
+// over CLOCK_GROUPS counters, each on its own 128-byte line (clock[CLOCK_SUB0 + 16 g]), so that a large grid's
+// exit atomics land on 32 addresses instead of one (same-address atomics serialise at ~2 ns each: 2 048 CTAs cost
+// catch 3 us per step; 64 per address cost 0.1 us).
+static const int CLOCK_GROUPS = 32, CLOCK_SUB0 = 16, CLOCK_WORDS = CLOCK_SUB0 + 16 * CLOCK_GROUPS;
+
 template <class F, int RK, bool kNoise, bool kTrack>
 __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kernel(const EnvParams p, const LaunchArgs a) {
   typedef typename RngOf<RK>::type R;
   constexpr int kEmit = EmitKind<F>::value;
   extern __shared__ float4 smem_raw[];
+  __shared__ MailFields mail_in;
+  __shared__ int mail_cancel;
   const int tid = threadIdx.x & 31, warp = threadIdx.x >> 5, warps_per_cta = blockDim.x >> 5;
   const int64_t B = p.batch;
   const int K = p.obs_numel;
-  const bool vec = a.obs_vec_ok != 0;
-  const size_t stage_floats = smem_floats_per_warp<F>(K, a.emit_bulk != 0, a.group_lanes);
+  const size_t stage_floats = smem_floats_per_warp<F>(K, a.emit_bulk != 0, a.group_lanes, a.stage_rows);
+  const unsigned row_mask = a.stage_rows == 2 ? 1u : 0u;      // row / board stage of store number n: n & row_mask
   float* stage = reinterpret_cast<float*>(smem_raw) + (size_t)warp * stage_floats;
+  // mnist bulk path: all-zero tiles shared by the CTA's warps (source of the LAST-frame stores), after the stages
+  float* cta_zero = reinterpret_cast<float*>(smem_raw) + (size_t)warps_per_cta * stage_floats;
 
   // Stages that rely on staying zero between steps are cleared once, before the dependency wait.
   if (kEmit == EMIT_TWOHOT || (kEmit == EMIT_ONEHOT && a.emit_bulk)) {
@@ -371,13 +503,50 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
   }
   if (kEmit == EMIT_IMAGE) {      // pixel table: image.astype(float32) / 255 for every int8 value (mnist.py:64)
     for (int i = tid; i < 256; i += 32) stage[i] = Mnist::pixel((int8_t)(uint8_t)i);
-    __syncwarp();
+    for (int i = threadIdx.x; i < a.cta_extra_floats; i += blockDim.x) cta_zero[i] = 0.f;
+    fence_proxy_async_smem();
+    __syncthreads();
   }
   // Wait for the previous step's kernel (it wrote the lane state read below), THEN allow the next step's kernel
   // to become resident: its CTAs park at their own wait, so at most one dependent grid is ever pending.
   if (a.use_pdl) { pdl_wait(); pdl_launch_dependents(); }
   int64_t step0 = a.step0;
   if (a.clock) step0 += (int64_t)*reinterpret_cast<volatile unsigned long long*>(a.clock);
+
+  // Caller-owned buffers: launch arguments, or -- doorbell mode -- whatever the host wrote into the mailbox
+  // before it rang this launch's ticket.
+  MailFields io;
+  io.actions = a.actions; io.obs = a.obs; io.reward = a.reward; io.reward_f64 = a.reward_f64;
+  io.discount = a.discount; io.step_type = a.step_type; io.obs_vec_ok = a.obs_vec_ok; io.pad = 0;
+  bool cancelled = false;
+  if (a.mailbox && a.wait_doorbell) {
+    if (threadIdx.x == 0) {
+      unsigned long long seen;
+      if (blockIdx.x == 0) {                 // the one poller of host memory
+        const unsigned long long deadline = global_timer_ns() + a.doorbell_timeout_ns;
+        do { seen = ld_sys_u64(&a.mailbox->doorbell); }
+        while ((seen & ~MAIL_CANCEL) < a.ticket && global_timer_ns() < deadline);
+        if ((seen & ~MAIL_CANCEL) < a.ticket) seen = a.ticket | MAIL_CANCEL;      // nobody rang: stand down
+        __threadfence_system();              // the fields were written before the doorbell
+        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&a.mailbox->in);
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(&a.mail->in);
+        for (int k = 0; k < (int)(sizeof(MailFields) / 8); ++k) dst[k] = ld_sys_u64(src + k);
+        __threadfence();
+        a.mail->relay = seen;
+      } else {
+        do { seen = a.mail->relay; } while ((seen & ~MAIL_CANCEL) < a.ticket);
+        __threadfence();
+      }
+      mail_cancel = (seen & MAIL_CANCEL) ? 1 : 0;
+      const volatile unsigned long long* src = reinterpret_cast<const volatile unsigned long long*>(&a.mail->in);
+      unsigned long long* dst = reinterpret_cast<unsigned long long*>(&mail_in);
+      for (int k = 0; k < (int)(sizeof(MailFields) / 8); ++k) dst[k] = src[k];
+    }
+    __syncthreads();
+    io = mail_in;
+    cancelled = mail_cancel != 0;
+  }
+  const bool vec = io.obs_vec_ok != 0;
 
   const int cl = a.chunk_lanes;
   const int64_t n_chunks = (B + cl - 1) / cl;
@@ -392,6 +561,11 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
     return total_warps + (int64_t)__shfl_sync(0xffffffffu, v, 0);
   };
   int64_t cur_chunk = (int64_t)blockIdx.x * warps_per_cta + warp;
+  if (cancelled) {
+    // A stood-down launch still owes the chunk counter its share: a launch over C chunks advances it by exactly C.
+    if (dynamic && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(a.work_counter, (unsigned long long)n_chunks);
+    cur_chunk = n_chunks;
+  }
 
   const bool has_rng = p.rng_pos != nullptr;
   // catch: cells this thread poked into stage buffer 0 / 1 (cleared when that buffer is reused)
@@ -413,7 +587,7 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
     if (kEmit == EMIT_ROWS) bulk = bulk && K >= 3 && ((n_lanes * K) & 3) == 0;
     if (kEmit == EMIT_TWOHOT) bulk = bulk && ((n_lanes * K) & 3) == 0;
     if (kEmit == EMIT_ONEHOT) bulk = bulk && ((K & 3) == 0 || ((n_lanes % a.group_lanes) == 0 && ((a.group_lanes * K) & 3) == 0));
-    if (kEmit == EMIT_IMAGE) bulk = false;
+    if (kEmit == EMIT_IMAGE) bulk = bulk && (K & 3) == 0;
     any_bulk = any_bulk || bulk;
 
     typename F::Lane L;
@@ -445,18 +619,27 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
       if (active) {
         int32_t action = 0;
         if (a.mode == MODE_STEP) {
-          action = a.actions ? a.actions[off]
-                             : action_stream.sample(a.action_seed, p.lane_offset + (uint64_t)lane, (uint64_t)(step0 + t), p.num_actions);
+          if (io.actions) {
+            // doorbell mode reads host memory the launch may have cached before the host wrote it: ld.cv
+            action = a.mailbox ? __ldcv(io.actions + off) : io.actions[off];
+            if ((uint32_t)action >= (uint32_t)p.num_actions) {      // never index a table or pack state with it
+              if (a.bad_action) *a.bad_action = 1;
+              action = action < 0 ? 0 : p.num_actions - 1;
+            }
+          } else {
+            action = action_stream.sample(a.action_seed, p.lane_offset + (uint64_t)lane, (uint64_t)(step0 + t), p.num_actions);
+          }
           if (a.actions_out) a.actions_out[off] = action;
         }
+        const bool after_last = L.nr != 0;
         const StepOut o = lane_transition<F, R, R>(p, lane, L, rng, wrng, action, a.mode, kNoise);
-        if (kTrack) ep.track(p, lane, o, step0 + t);
-        if (a.reward) a.reward[off] = (float)o.reward;
-        if (a.reward_f64) a.reward_f64[off] = o.reward;
-        if (a.discount) a.discount[off] = o.discount;
-        if (a.step_type) a.step_type[off] = o.step_type;
+        if (kTrack) ep.track(p, lane, o, step0 + t, after_last);
+        if (io.reward) io.reward[off] = (float)o.reward;
+        if (io.reward_f64) io.reward_f64[off] = o.reward;
+        if (io.discount) io.discount[off] = o.discount;
+        if (io.step_type) io.step_type[off] = o.step_type;
       }
-      float* obs_t = a.obs + t * B * (int64_t)K;
+      float* obs_t = io.obs + t * B * (int64_t)K;
 
       if (kEmit == EMIT_ONEHOT) {
         const int hot = Descriptor<F>::a(L);
@@ -495,9 +678,9 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
       } else if (kEmit == EMIT_TWOHOT) {
         const int hot_a = Descriptor<F>::a(L), hot_b = Descriptor<F>::b(L);
         if (bulk) {
-          const int buf = (int)(emitted & 1u);
+          const int buf = (int)(emitted & row_mask);
           float* boards = stage + (size_t)buf * 32 * K;
-          if (tid == 0) bulk_wait_read<ROW_STAGES - 1>();      // the store that last read `boards` is done with it
+          if (tid == 0) { if (row_mask) bulk_wait_read<1>(); else bulk_wait_read<0>(); }   // the store that last read `boards` is done with it
           __syncwarp();
           float* mine = boards + tid * K;
           const int old_a = buf ? poked_a1 : poked_a0, old_b = buf ? poked_b1 : poked_b0;
@@ -514,10 +697,15 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
           emit_twohot_vec(obs_t, warp_base, n_lanes, K, hot_a, hot_b, vec);
         }
       } else if (kEmit == EMIT_IMAGE) {
-        emit_image(p, stage, obs_t, warp_base, n_lanes, K, Descriptor<F>::a(L), vec && (K & 3) == 0);
+        const int image = Descriptor<F>::a(L);
+        if (bulk) emit_image_bulk(p, stage, cta_zero, obs_t, warp_base, n_lanes, K, active ? image : -1, a.group_lanes, a.l2_hint, emitted);
+        else emit_image(p, stage, obs_t, warp_base, n_lanes, K, image, vec && (K & 3) == 0);
+      } else if (!a.stage_rows) {
+        // observation rows too long for a shared-memory stage: every thread renders its row in place
+        if (active) RowRenderer<F, R>::run(p, L, rng, obs_t + lane * (int64_t)K);
       } else {
-        float* rows = stage + (size_t)(emitted & 1u) * 32 * K;
-        if (bulk) { if (tid == 0) bulk_wait_read<ROW_STAGES - 1>(); }
+        float* rows = stage + (size_t)(emitted & row_mask) * 32 * K;
+        if (bulk) { if (tid == 0) { if (row_mask) bulk_wait_read<1>(); else bulk_wait_read<0>(); } }
         __syncwarp();
         if (active) RowRenderer<F, R>::run(p, L, rng, rows + tid * K);
         if (bulk) {
@@ -540,16 +728,37 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
     }
     if (dynamic && lazy) cur_chunk = fetch_chunk();        // lazy: nothing was reserved while working
   }
-  if (any_bulk && tid == 0) bulk_wait_read<0>();      // shared memory must outlive the last bulk read
-  if (a.clock && !a.clock_external) {
+  if (any_bulk && tid == 0) {
+    // shared memory must outlive the last bulk read; in doorbell mode the host takes `done` to mean that the
+    // observations are in device memory, so there the stores themselves must have completed
+    if (a.mailbox) bulk_wait_all(); else bulk_wait_read<0>();
+  }
+  if (a.mailbox) {
+    __threadfence_system();                  // every thread: its zero-copy outputs are visible to the host ...
+    __syncthreads();                         // ... before the CTA counts itself finished
+    if (threadIdx.x == 0) {
+      if (atomicAdd(&a.mail->finished, 1ull) == (unsigned long long)gridDim.x - 1ull) {
+        a.mail->finished = 0ull;
+        __threadfence_system();
+        st_sys_u64(&a.mailbox->done, a.ticket | (cancelled ? MAIL_CANCEL : 0ull));
+      }
+    }
+  }
+  if (a.clock) {
     __syncthreads();
     if (threadIdx.x == 0) {
+      const unsigned groups = gridDim.x < (unsigned)CLOCK_GROUPS ? gridDim.x : (unsigned)CLOCK_GROUPS;
+      const unsigned g = blockIdx.x % groups;
+      const unsigned members = gridDim.x / groups + (g < gridDim.x % groups ? 1u : 0u);
+      unsigned long long* sub = a.clock + CLOCK_SUB0 + 16 * g;
       __threadfence();
-      if (atomicAdd(a.clock + 2, 1ull) == (unsigned long long)gridDim.x - 1ull) {
-        a.clock[0] = (unsigned long long)(step0 - a.step0) + (a.mode == MODE_INIT ? 0ull : (unsigned long long)a.T);
-        a.clock[1] = 0ull;
-        a.clock[2] = 0ull;
-        __threadfence();
+      if (atomicAdd(sub, 1ull) == (unsigned long long)members - 1ull) {
+        *sub = 0ull;                          // re-armed for the next launch (which starts after this one ends)
+        if (atomicAdd(a.clock + 2, 1ull) == (unsigned long long)groups - 1ull) {
+          a.clock[0] = (unsigned long long)(step0 - a.step0) + (a.mode == MODE_INIT ? 0ull : (unsigned long long)a.T);
+          a.clock[1] = 0ull;
+          a.clock[2] = 0ull;
+        }
       }
     }
   }

@@ -9,6 +9,9 @@ per-rank block of Logging statistics at log points (NCCL on GPUs; gloo in the CP
 
 from typing import Any, Dict, Optional, Tuple
 
+import ctypes
+
+from bsuite_b200 import _lib
 from bsuite_b200 import registry
 
 
@@ -92,6 +95,10 @@ class LogPoint:
     self._ready = [torch.cuda.Event() for _ in range(self._slots)] if self._side is not None else None
     self._done = [torch.cuda.Event() for _ in range(self._slots)] if self._cuda else None
     self._issued = 0
+    for env in self.envs:
+      if not env._track:  # pylint: disable=protected-access
+        raise RuntimeError('create the environments with track_episodes=True')
+    self._handles = (ctypes.c_void_p * len(self.envs))(*[env._handle.ptr.value for env in self.envs])  # pylint: disable=protected-access
 
   def issue(self) -> int:
     torch = self._torch
@@ -102,8 +109,11 @@ class LogPoint:
     if self._side is not None and ticket >= self._slots:
       current.wait_event(self._done[slot])          # the gather that last read this slot's block has finished
     block = self._local[slot]
-    for i, env in enumerate(self.envs):
-      env.episode_stat_sums(out=block[i])
+    if len(self.envs) == 1:
+      self.envs[0].episode_stat_sums(out=block[0])
+    else:                                            # every environment in ONE reduction launch
+      first = self.envs[0]
+      _lib.check(first._lib.bsb_sum_episode_stats_many(self._handles, len(self.envs), block.data_ptr(), first._stream()))  # pylint: disable=protected-access
     if self.world == 1:
       if self._cuda:
         self._done[slot].record(current)

@@ -173,11 +173,14 @@ class BatchedEnvironment:
     if rng not in ('philox', 'mt19937'):
       raise ValueError(f'rng must be "philox" or "mt19937", got {rng!r}')
     self._rng_kind = _lib.RNG_PHILOX if rng == 'philox' else _lib.RNG_MT19937
-    seed = spec.seed if spec.seed is not None else seed
+    # An explicit engine `seed` wins; otherwise the experiment's own default (memory_len, memory_size and
+    # umbrella_distract fix seed=0: experiments/memory_len/memory_len.py:31-37), otherwise OS entropy.
+    seed = seed if seed is not None else spec.seed
     self._seed = _fresh_seed() if seed is None else int(seed)
     if self._rng_kind == _lib.RNG_MT19937 and not 0 <= self._seed < 2**32:
       raise ValueError('Seed must be between 0 and 2**32 - 1')   # numpy's own message
     self._lane_offset = int(lane_offset)
+    self._async_work = False        # something was enqueued on a torch stream since the last host-driven step
     flags = _lib.FLAG_TRACK_EPISODES if track_episodes else 0
     self._track = bool(track_episodes)
     self._reward_dtype = torch.float64 if str(reward_dtype).endswith('64') else torch.float32
@@ -244,6 +247,7 @@ class BatchedEnvironment:
     """base.Environment.reset for every lane (base.py:54-57)."""
     out = out or self.make_buffers()
     outputs = out.as_outputs()
+    self._async_work = True
     _lib.check(self._lib.bsb_reset(self._handle.ptr, ctypes.byref(outputs), self._stream()))
     return out.timestep()
 
@@ -259,6 +263,7 @@ class BatchedEnvironment:
       actions = self._device_actions(actions, (self._batch,))
     if out is None:
       out = self.make_buffers()
+    self._async_work = True
     status = self._lib.bsb_step(self._handle.ptr, actions.data_ptr(), ctypes.byref(out.as_outputs()), self._stream())
     if status:
       _lib.check(status)
@@ -295,11 +300,23 @@ class BatchedEnvironment:
                    if with_observation else None)
     return StepBuffers(observation=observation, reward=reward, discount=discount, step_type=step_type)
 
-  def step_host(self, actions, host: StepBuffers, out: Optional[StepBuffers] = None):
-    """One step driven from HOST memory through `bsb_step_host`: actions (CPU int32 tensor, ideally pinned) are
-    copied to the device, the transition kernel runs, and reward / discount / step_type (and the observation if
-    `host.observation` is set) are copied back into `host`; returns after everything has landed.  Observations
-    are also left on the device in `out.observation` for the agent.  Returns (host TimeStep, device observation).
+  def step_host(self, actions, host: StepBuffers, out: Optional[StepBuffers] = None, prelaunch: bool = False):
+    """One step driven from HOST memory through `bsb_step_host`: the reference's call pattern, one
+    `env.step(action)` per decision (baselines/experiment.py:45-57), for agents whose policy runs on the host.
+
+    `actions`: CPU int32 tensor [batch] (ideally pinned: the kernel then reads it in place over PCIe); reward /
+    discount / step_type (and the observation if `host.observation` is set) are delivered into `host`; the call
+    returns after everything has landed.  Observations are also left on the device in `out.observation` for the
+    agent.  Returns (host TimeStep, device observation).  Actions outside [0, num_actions) raise `EngineError`.
+
+    Stream order: the step runs on a stream the handle owns.  Work enqueued earlier on this environment through
+    `reset()` / `step()` / `rollout()` on the current torch stream is waited for on the device (the handle's
+    stream is fenced behind the current stream the first time a host-driven step follows such work).
+
+    `prelaunch=True` (pinned buffers, CUDA): the next step's kernel is queued immediately and waits for this
+    method's next call on a doorbell in pinned memory, so a call costs neither a kernel launch nor a stream
+    synchronise.  The waiting kernel occupies the GPU: use it for host-side policies in a tight loop; any other
+    method of this environment (or 200 ms without a call) stands it down.
     """
     torch = self._torch
     if not (type(actions) is torch.Tensor and actions.dtype is torch.int32 and actions.device.type == 'cpu'
@@ -316,12 +333,32 @@ class BatchedEnvironment:
     if self._ordinal < 0:        # host environment: one memory space; `out.observation` is the observation
       houts = _lib.Outputs.from_buffer_copy(houts)
       houts.observation = out.observation.data_ptr()
-    status = self._lib.bsb_step_host(self._handle.ptr, actions.data_ptr(), ctypes.byref(houts), dev_obs)
+    flags = _lib.HOST_PRELAUNCH if prelaunch else 0
+    stream = None
+    if self._async_work and self._ordinal >= 0:
+      flags |= _lib.HOST_ORDER_AFTER_STREAM
+      stream = self._stream()
+      self._async_work = False
+    status = self._lib.bsb_step_host(self._handle.ptr, actions.data_ptr(), ctypes.byref(houts), dev_obs, stream, flags)
     if status:
       _lib.check(status)
     if self._ordinal < 0 and host.observation is not None:
       host.observation.copy_(out.observation)
     return host.timestep(), out.observation
+
+  def host_flush(self):
+    """Stands down a kernel queued by `step_host(..., prelaunch=True)` (every other method does so implicitly)."""
+    _lib.check(self._lib.bsb_host_flush(self._handle.ptr))
+
+  def invalid_actions_seen(self) -> bool:
+    """True if a DEVICE-resident action tensor passed to `step()` / `rollout()` since the last call held a value
+    outside [0, num_actions): the kernels clamp such actions before any table lookup and raise a flag (host
+    actions are rejected up front instead).  Synchronises the current stream."""
+    if self._ordinal >= 0:
+      self._torch.cuda.current_stream(self._device).synchronize()
+    seen = ctypes.c_int32()
+    _lib.check(self._lib.bsb_invalid_actions(self._handle.ptr, ctypes.byref(seen)))
+    return bool(seen.value)
 
   def rollout(self, num_steps: int, actions=None, action_seed: int = 0, out: Optional[StepBuffers] = None):
     """`num_steps` fused step() calls; actions [T,B] or None for on-device uniform random actions.
@@ -336,6 +373,7 @@ class BatchedEnvironment:
       act_ptr = ctypes.c_void_p(actions.data_ptr())
     outputs = out.as_outputs()
     act_out = ctypes.c_void_p(out.actions.data_ptr()) if out.actions is not None else None
+    self._async_work = True
     _lib.check(self._lib.bsb_rollout(self._handle.ptr, num_steps, act_ptr, int(action_seed) & _MASK64,
                                      ctypes.byref(outputs), act_out, self._stream()))
     return out.timestep()
@@ -434,15 +472,28 @@ class BatchedEnvironment:
     blob = np.empty(n.value, dtype=np.uint8)
     _lib.check(self._lib.bsb_get_state(self._handle.ptr, ctypes.c_void_p(blob.ctypes.data), n.value, self._stream()))
     return dict(blob=blob, batch=self._batch, seed=self._seed, lane_offset=self._lane_offset,
-                family=self._spec.family)
+                family=self._spec.family, config=self._config_fingerprint())
 
   def load_state_dict(self, state: Dict[str, Any]):
     if (state['batch'], state['family']) != (self._batch, self._spec.family):
       raise ValueError('state_dict belongs to a different environment')
     if (state['seed'], state['lane_offset']) != (self._seed, self._lane_offset):
       raise ValueError('state_dict was taken with different (seed, lane_offset); RNG keys would not match')
+    if state.get('config', self._config_fingerprint()) != self._config_fingerprint():
+      raise ValueError('state_dict was taken from a differently configured environment (fields, wrapper, rng or tracking differ)')
     blob = np.ascontiguousarray(state['blob'], dtype=np.uint8)
     _lib.check(self._lib.bsb_set_state(self._handle.ptr, ctypes.c_void_p(blob.ctypes.data), blob.nbytes, self._stream()))
+
+  def _config_fingerprint(self) -> str:
+    """Everything that shapes the meaning of the snapshot bytes besides (batch, family, seed, lane_offset)."""
+    import hashlib
+    h = hashlib.sha256()
+    h.update(repr((sorted(self._spec.fields.items()), self._spec.wrapper, self._rng_kind, self._track,
+                   tuple(self._spec.obs_shape), self._spec.num_actions)).encode())
+    for table in (self._spec.table, self._spec.table2):
+      if table is not None:
+        h.update(np.ascontiguousarray(table).tobytes())
+    return h.hexdigest()[:16]
 
   def close(self):
     self._handle.close()
@@ -460,7 +511,7 @@ class DmEnvAdapter(dm_env.Environment):
   def __init__(self, spec: EnvSpec, device='cuda', seed: Optional[int] = None, rng: Optional[str] = None):
     self._spec = spec
     self._ordinal = _resolve_device(device)
-    seed = spec.seed if spec.seed is not None else seed
+    seed = seed if seed is not None else spec.seed
     if rng is None:
       rng = 'mt19937'   # numpy.random.RandomState(seed): the unpatched reference's stream
     self._seed = _fresh_seed() if seed is None else int(seed)
@@ -485,6 +536,7 @@ class DmEnvAdapter(dm_env.Environment):
     self._outputs.discount = self._discount.ctypes.data
     self._outputs.step_type = self._step_type.ctypes.data
     self._dev = None
+    self._reset_stream, self._host_flags = None, 0   # the next host step is fenced behind the stream reset() used
     if self._ordinal >= 0:   # device-side scratch for reset(); step() uses bsb_step_host
       import torch
       device_t = torch.device('cuda', self._ordinal)
@@ -508,6 +560,7 @@ class DmEnvAdapter(dm_env.Environment):
       import torch
       outputs = self._dev.as_outputs()
       stream = ctypes.c_void_p(torch.cuda.current_stream(self._dev.observation.device).cuda_stream)
+      self._reset_stream, self._host_flags = stream, _lib.HOST_ORDER_AFTER_STREAM
       _lib.check(self._lib.bsb_reset(self._handle.ptr, ctypes.byref(outputs), stream))
       self._obs[:] = self._dev.observation.cpu().numpy()
       self._reward[:] = self._dev.reward.cpu().numpy()
@@ -516,13 +569,19 @@ class DmEnvAdapter(dm_env.Environment):
     return self._timestep()
 
   def step(self, action):
-    self._action[0] = int(action)
+    action = int(action)
+    if not 0 <= action < self._spec.num_actions:
+      # the reference indexes a table with the action and fails with IndexError (bandit.py:61, catch.py:84) or
+      # silently takes "the other" branch (deep_sea.py:118); an action_spec violation is an error here
+      raise ValueError(f'action {action} is outside the action_spec: DiscreteArray(num_values={self._spec.num_actions})')
+    self._action[0] = action
     if self._ordinal < 0:
       _lib.check(self._lib.bsb_step(self._handle.ptr, ctypes.c_void_p(self._action.ctypes.data),
                                     ctypes.byref(self._outputs), None))
     else:
       _lib.check(self._lib.bsb_step_host(self._handle.ptr, ctypes.c_void_p(self._action.ctypes.data),
-                                         ctypes.byref(self._outputs), None))
+                                         ctypes.byref(self._outputs), None, self._reset_stream, self._host_flags))
+      self._host_flags = 0
     return self._timestep()
 
   def observation_spec(self):

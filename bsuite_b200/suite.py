@@ -32,6 +32,19 @@ def algorithmic_bytes_per_lane_step(env) -> int:
   return 4 * numel + 16 + _STATE_BYTES.get(env.family, 16)
 
 
+class GraphedSweep:
+  """Captured lock-step(s) of a `SweepBatch` (`SweepBatch.capture`): `replay()` returns id -> TimeStep (a list of
+  them, one per captured lock-step, when several were captured) -- the same tensors every time, leading axis =
+  the captured number of steps."""
+
+  def __init__(self, graph, timesteps):
+    self.graph, self.timesteps = graph, timesteps
+
+  def replay(self):
+    self.graph.replay()
+    return self.timesteps
+
+
 class SweepBatch:
 
   def __init__(self, bsuite_ids: Optional[Sequence[str]] = None, lanes: int = 4096, device='cuda', seed: int = 0,
@@ -74,7 +87,7 @@ class SweepBatch:
     slot = self._turn % self._ring
     self._turn += 1
     result = {}
-    if not self._cuda:
+    if not self._cuda or len(self.envs) == 1:      # nothing to overlap: stay on the caller's stream
       for k, env in self.envs.items():
         result[k] = env.rollout(num_steps, action_seed=action_seed, out=self._buffers[k][slot])
       return result
@@ -87,6 +100,30 @@ class SweepBatch:
     for stream in self._streams.values():
       current.wait_stream(stream)
     return result
+
+  def capture(self, num_steps: int = 1, action_seed: int = 0, lock_steps: int = 1) -> 'GraphedSweep':
+    """Records `lock_steps` successive lock-steps of every id (a `num_steps`-step rollout each, on-device actions)
+    into a single CUDA graph: the per-id launches fork from the capturing stream onto the ids' streams and join
+    again, so a replay costs one `cudaGraphLaunch` instead of one launch per id and lock-step -- 23 launches per
+    lock-step are launch-bound when each id holds a few hundred lanes (BASELINE config #5 sharded over 8 GPUs).
+    Each captured lock-step writes its own output buffer set.  The environments keep their step counters on the
+    device from here on (graph-safe mode), so replays and eager rollouts can be mixed."""
+    torch = self._torch
+    if not self._cuda:
+      raise RuntimeError('CUDA graphs need CUDA environments')
+    lock_steps = max(1, int(lock_steps))
+    self.set_ring(lock_steps)
+    self._turn = 0
+    states = {k: env.state_dict() for k, env in self.envs.items()}
+    self.rollout(num_steps, action_seed=action_seed)      # eager pass: module loading and function attributes
+    torch.cuda.synchronize(self._device)
+    for k, env in self.envs.items():
+      env.load_state_dict(states[k])
+    self._turn = 0
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+      results = [self.rollout(num_steps, action_seed=action_seed) for _ in range(lock_steps)]
+    return GraphedSweep(graph, results[0] if lock_steps == 1 else results)
 
   def set_ring(self, ring: int):
     """Number of output buffer sets successive rollouts cycle through (drops the current buffers)."""

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define BSB_ABI_VERSION 4
+#define BSB_ABI_VERSION 5
 #define BSB_DEVICE_HOST (-1)
 #define BSB_MAX_INFO 4
 
@@ -241,7 +241,7 @@ int32_t bsb_read_episode_stats(bsb_env* env, int32_t field, double* dst,
  * memory, for good: replays and eager calls can then be mixed in any order, and bsb_steps_done / bsb_get_state
  * synchronise the device to read the counter back.  Consecutive captured steps keep their programmatic dependent
  * launch (it becomes a programmatic graph edge; BSB_GRAPH_PDL=0 turns that off).
- * bsb_step_host (internal streams and a host synchronise) cannot be captured.
+ * bsb_step_host (internal stream, host-side wait) cannot be captured.
  */
 
 /*
@@ -253,6 +253,12 @@ int32_t bsb_read_episode_stats(bsb_env* env, int32_t field, double* dst,
  */
 int32_t bsb_sum_episode_stats(bsb_env* env, double* dst5, void* stream);
 
+/* The same reduction for `count` environments of one device in ONE kernel launch:
+ * dst receives [count][5].  A log point of a whole sweep (bsuite/sweep.py:134-150:
+ * 23 experiments) is then one launch and one all-gather. */
+int32_t bsb_sum_episode_stats_many(bsb_env* const* envs, int32_t count,
+                                   double* dst, void* stream);
+
 /* Flat snapshot of all lane state (checkpoint/resume; absent in the reference). */
 int32_t bsb_state_bytes(const bsb_env* env, int64_t* nbytes);
 int32_t bsb_get_state(bsb_env* env, void* dst_host, int64_t nbytes, void* stream);
@@ -260,21 +266,55 @@ int32_t bsb_set_state(bsb_env* env, const void* src_host, int64_t nbytes,
                       void* stream);
 
 /*
- * Host-buffer convenience for FFI callers without a device allocator: copies
- * `actions` (host, int32 [B]) to the device, steps, and copies the requested
- * outputs back into HOST buffers (`host_out`; NULL members are skipped, so an
- * agent that consumes observations on the device passes observation = NULL and
- * supplies `device_obs`, a device pointer that receives them).  Synchronous.
+ * Host-buffer convenience for FFI callers without a device allocator: takes
+ * `actions` (host, int32 [B]), steps, and delivers the requested outputs into
+ * HOST buffers (`host_out`; NULL members are skipped, so an agent that consumes
+ * observations on the device passes observation = NULL and supplies
+ * `device_obs`, a device pointer that receives them).  Synchronous: on return
+ * the outputs have landed and `device_obs` is complete in device memory.  This
+ * is the call pattern of the reference's agent loop, one env.step(action) per
+ * decision (baselines/experiment.py:45-57).
+ *
  * When `actions` and the requested scalar outputs are PINNED host memory the
  * kernel accesses them in place over PCIe (zero-copy: no separate H2D / D2H
- * copies); pageable buffers take the staged-copy path.
- * Stream order: the work runs on a stream the handle owns and is complete on
- * return, so later calls on any stream see its results; work enqueued EARLIER
- * on this handle through bsb_step / bsb_rollout on a caller's stream is not
- * waited for -- synchronise that stream first if there is any in flight.
+ * copies) and signals completion through a pinned mailbox word the host spins
+ * on (no stream synchronise; BSB_HOST_SPIN=0 restores it); pageable buffers
+ * take the staged-copy path.  Host actions are range-checked: an action outside
+ * [0, num_actions) yields BSB_INVALID_ARGUMENT (the reference raises IndexError,
+ * e.g. bandit.py:61).
+ *
+ * flags
+ *   BSB_HOST_ORDER_AFTER_STREAM  work enqueued EARLIER on this handle through
+ *       bsb_reset / bsb_step / bsb_rollout on `caller_stream` is waited for (on
+ *       the device) before the step runs.  Without the flag the caller must
+ *       have synchronised that stream: the step runs on a stream the handle owns.
+ *   BSB_HOST_PRELAUNCH  (pinned buffers only) after ringing this step, the NEXT
+ *       step's kernel is enqueued at once; it becomes resident as this one drains
+ *       and polls the mailbox doorbell, so the next call costs neither a launch
+ *       nor a wake-up -- for agents whose policy runs on the HOST.  While it
+ *       waits it occupies the SMs: other GPU work of the process queues behind it
+ *       until the next call, bsb_host_flush, or BSB_DOORBELL_TIMEOUT_MS (default
+ *       200) without a ring, after which it stands down by itself.  Every other
+ *       entry point of this handle stands it down first.
  */
+#define BSB_HOST_ORDER_AFTER_STREAM 1u
+#define BSB_HOST_PRELAUNCH 2u
 int32_t bsb_step_host(bsb_env* env, const int32_t* actions,
-                      const bsb_outputs* host_out, float* device_obs);
+                      const bsb_outputs* host_out, float* device_obs,
+                      void* caller_stream, uint32_t flags);
+
+/* Stands down a launch queued by BSB_HOST_PRELAUNCH (no-op otherwise). */
+int32_t bsb_host_flush(bsb_env* env);
+
+/*
+ * Out-of-range actions.  Host-resident actions (host environments,
+ * bsb_step_host) are validated before anything moves.  Device-resident action
+ * tensors cannot be inspected without a synchronise: the kernels clamp such an
+ * action into [0, num_actions) before it indexes a table or is packed into lane
+ * state, and raise a flag.  *seen receives the flag (1 = some action since the
+ * last call was out of range) and clears it; synchronise the stream first.
+ */
+int32_t bsb_invalid_actions(bsb_env* env, int32_t* seen);
 
 /* Number of kernels this library has launched in this process (bench evidence). */
 int64_t bsb_launch_count(void);

@@ -142,3 +142,24 @@ def test_log_point_inside_a_graph():
     eager_env.rollout(T, action_seed=3)
     assert torch.equal(sums, eager_env.episode_stat_sums())
   assert float(sums[0]) > 0
+
+
+def test_sweep_lock_step_captured_in_one_graph_equals_eager_rollouts(mnist_dir):
+  """SweepBatch.capture: every id's launch in ONE graph (fork / join over the ids' streams); replays must equal an
+  uncaptured twin bit for bit, and mix with eager rollouts."""
+  from bsuite_b200 import suite
+  ids = ['catch/0', 'deep_sea/0', 'bandit_noise/0', 'cartpole/0', 'mnist/0', 'umbrella_length/0', 'memory_size/0']
+  a = suite.SweepBatch(ids, lanes=512, device='cuda', seed=1)
+  b = suite.SweepBatch(ids, lanes=512, device='cuda', seed=1)
+  graphed = a.capture(num_steps=1)
+  for round_ in range(40):
+    got = graphed.replay()
+    want = b.rollout(1)
+    torch.cuda.synchronize()
+    for k in ids:
+      for field in ('step_type', 'reward', 'discount', 'observation'):
+        assert torch.equal(getattr(got[k], field), getattr(want[k], field)), (round_, k, field)
+    if round_ == 17:                     # an eager rollout in between
+      a.rollout(3); b.rollout(3)
+  assert torch.equal(a.gather_returns(), b.gather_returns())
+  a.close(); b.close()

@@ -12,7 +12,7 @@ import torch
 import bsuite_b200
 
 for bsuite_id, batch in (('deep_sea/11', 20000), ('deep_sea_stochastic/3', 40001), ('catch_noise/0', 5000), ('cartpole/0', 3000),
-                         ('umbrella_length/3', 2000), ('mnist/0', 1500)):
+                         ('umbrella_length/3', 2000), ('umbrella_distract/22', 1500), ('mnist/0', 1500), ('mnist/0', 30000)):
   if bsuite_id.startswith('mnist'):
     from bsuite_b200 import datasets
     os.environ[datasets.ENV_VAR] = datasets.write_synthetic_mnist('/tmp/bsb_sanitize_mnist', 256, 16, 0)
@@ -44,4 +44,34 @@ for bsuite_id, batch in (('deep_sea/11', 20000), ('catch/0', 5000)):
   assert torch.equal(env.episode_stat_sums(), twin.episode_stat_sums()) and env.steps_done == twin.steps_done == 7
   print(bsuite_id, batch, 'graph replay == eager: True', flush=True)
   env.close(); twin.close()
+# Host-driven steps: completion through the pinned mailbox, pre-launched doorbell kernels (under the sanitizer launches
+# are serialised, so a pre-launched kernel times out and stands down: the cancel path), out-of-range actions.
+for bsuite_id, batch in (('deep_sea/11', 20000), ('catch/0', 3000), ('mnist/0', 1500)):
+  env = bsuite_b200.load_from_id(bsuite_id, batch=batch, device='cuda', seed=3, track_episodes=True)
+  twin = bsuite_b200.load_from_id(bsuite_id, batch=batch, device='cuda', seed=3, track_episodes=True)
+  host = env.make_host_buffers()
+  acts = torch.as_tensor(env.random_actions(6, action_seed=1, first_step=0)).pin_memory()
+  env.reset(); twin.reset()
+  for t in range(6):
+    got, obs = env.step_host(acts[t], host, prelaunch=(t >= 3))
+    want = twin.step(acts[t].cuda())
+    torch.cuda.synchronize()
+    assert torch.equal(obs, want.observation) and torch.equal(got.reward, want.reward.cpu()) and torch.equal(got.step_type, want.step_type.cpu())
+  bad = acts[0].cuda().clone(); bad[5] = 99
+  env.step(bad); twin.step(bad.clamp(max=env.num_actions - 1))
+  assert env.invalid_actions_seen() and torch.equal(env.episode_stat_sums(), twin.episode_stat_sums())
+  print(bsuite_id, batch, 'host-driven steps == ordinary steps: True', flush=True)
+  env.close(); twin.close()
+# One-launch reduction over several environments and a whole lock-step in one graph.
+from bsuite_b200 import suite
+ids = ['catch/0', 'deep_sea/0', 'bandit_noise/0', 'cartpole/0', 'mnist/0', 'umbrella_length/0']
+a, b = suite.SweepBatch(ids, lanes=300, device='cuda', seed=1), suite.SweepBatch(ids, lanes=300, device='cuda', seed=1)
+graphed = a.capture(1, lock_steps=2)
+for _ in range(3):
+  got, want = graphed.replay(), [b.rollout(1), b.rollout(1)]
+  torch.cuda.synchronize()
+  assert all(torch.equal(got[i][k].observation, want[i][k].observation) for i in range(2) for k in ids)
+assert torch.equal(a.gather_returns(), b.local_returns().unsqueeze(0))
+print('sweep graph == eager, one-launch reduction == per-id reductions: True', flush=True)
+a.close(); b.close()
 print('sanitize workload finished')
