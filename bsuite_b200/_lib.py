@@ -27,7 +27,7 @@ WRAP_NONE, WRAP_REWARD_NOISE, WRAP_REWARD_SCALE = range(3)
 # enum bsb_rng_kind
 RNG_PHILOX, RNG_MT19937 = range(2)
 FLAG_TRACK_EPISODES = 1
-HOST_ORDER_AFTER_STREAM, HOST_PRELAUNCH = 1, 2      # bsb_step_host flags
+HOST_ORDER_AFTER_STREAM, HOST_PRELAUNCH, HOST_FENCE_CALLER = 1, 2, 4      # bsb_step_host flags
 EPISODE_STAT_FIELDS = ('steps', 'episode', 'total_return', 'episode_len', 'episode_return')
 
 
@@ -49,6 +49,7 @@ class Config(ctypes.Structure):
       ('noise_scale', ctypes.c_double), ('reward_scale', ctypes.c_double),
       ('table', ctypes.c_void_p), ('table_bytes', ctypes.c_int64),
       ('table2', ctypes.c_void_p), ('table2_bytes', ctypes.c_int64),
+      ('log_schedule', ctypes.c_void_p), ('log_schedule_len', ctypes.c_int64),
   ]
 
 
@@ -83,6 +84,8 @@ EXPORTS = {
     'bsb_sum_episode_stats': (ctypes.c_int32, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     'bsb_sum_episode_stats_many': (ctypes.c_int32, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int32, ctypes.c_void_p,
                                                     ctypes.c_void_p]),
+    'bsb_log_layout': (ctypes.c_int32, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]),
+    'bsb_read_log_rows': (ctypes.c_int32, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     'bsb_state_bytes': (ctypes.c_int32, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]),
     'bsb_get_state': (ctypes.c_int32, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
     'bsb_set_state': (ctypes.c_int32, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),

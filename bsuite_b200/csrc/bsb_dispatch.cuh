@@ -65,7 +65,13 @@ void host_run(const EnvParams& p, const LaunchArgs& a) {
       }
       const bool after_last = L.nr != 0;
       const StepOut o = lane_transition<F, R, R>(p, lane, L, rng, wrng, action, a.mode, noise);
-      if (track) ep.track(p, lane, o, a.step0 + t, after_last);
+      if (track) {
+        ep.track(p, lane, o, a.step0 + t, after_last);
+        if (p.log_rows && o.step_type == LAST && log_row_due(p, lane)) {
+          F::store(p, lane, L); ep.store(p, lane);
+          log_row_write(p, lane, a.step0 + t + 1);
+        }
+      }
       if (a.reward) a.reward[off] = (float)o.reward;
       if (a.reward_f64) a.reward_f64[off] = o.reward;
       if (a.discount) a.discount[off] = o.discount;

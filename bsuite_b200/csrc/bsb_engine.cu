@@ -157,6 +157,14 @@ int validate(const bsb_config& c, int64_t batch, int* obs_rows, int* obs_cols, i
       *obs_rows = c.image_rows; *obs_cols = c.image_cols; *n_actions = 10; break;
     default: return fail(BSB_INVALID_ARGUMENT, "unknown family");
   }
+  if (c.log_schedule_len < 0 || c.log_schedule_len > 4096) return fail(BSB_INVALID_ARGUMENT, "log_schedule_len must be in [0, 4096]");
+  if (c.log_schedule_len > 0) {
+    if (!c.log_schedule) return fail(BSB_INVALID_ARGUMENT, "log_schedule_len > 0 needs a log_schedule");
+    if (!(c.flags & BSB_FLAG_TRACK_EPISODES)) return fail(BSB_INVALID_ARGUMENT, "a log schedule needs BSB_FLAG_TRACK_EPISODES");
+    for (int64_t k = 0; k < c.log_schedule_len; ++k)
+      if (c.log_schedule[k] < 1 || (k > 0 && c.log_schedule[k] <= c.log_schedule[k - 1]))
+        return fail(BSB_INVALID_ARGUMENT, "log_schedule must be positive and strictly ascending");
+  }
   return BSB_OK;
 }
 
@@ -213,6 +221,8 @@ int mailbox_open(bsb_env* e) {
 
 // Enqueues one single-step launch that signals `ticket` through the mailbox.  wait_doorbell: the launch takes its
 // buffers from the mailbox once the host rings `ticket` (pre-launch); otherwise from `fields` right away.
+bool family_obs_from_state(const bsb_env* e) { return e->p.family == BSB_DEEP_SEA || e->p.family == BSB_CATCH; }
+
 int mailbox_launch(bsb_env* e, unsigned long long ticket, int64_t step0, const MailFields* fields, bool wait_doorbell) {
   LaunchArgs a;
   memset(&a, 0, sizeof(a));
@@ -223,6 +233,8 @@ int mailbox_launch(bsb_env* e, unsigned long long ticket, int64_t step0, const M
   a.T = 1; a.step0 = step0; a.mode = MODE_STEP;
   a.mailbox = e->mailbox_dev; a.mail = e->mail; a.ticket = ticket; a.wait_doorbell = wait_doorbell ? 1 : 0;
   a.doorbell_timeout_ns = e->doorbell_timeout_ns;
+  a.early_scalars = (e->host_early && family_obs_from_state(e)) ? 1 : 0;
+  if (a.early_scalars) e->early_inflight = true;
   return run(e, a, e->copy_stream);
 }
 
@@ -258,8 +270,22 @@ int flush_pending(bsb_env* e) {
   return mailbox_wait(e, ticket, &cancelled);
 }
 
+// Two-phase host steps return when the scalars have landed; the observation stores of the latest one may still
+// be in flight on the handle's stream.  Anything that leaves that stream (work on a caller's stream, state reads,
+// destruction) waits for it here.
+int drain_host_steps(bsb_env* e) {
+  int rc = flush_pending(e);
+  if (rc != BSB_OK) return rc;
+  if (e && e->device >= 0 && e->early_inflight) {
+    DeviceGuard guard(e->device);
+    e->early_inflight = false;
+    BSB_CUDA(cudaStreamSynchronize(e->copy_stream));
+  }
+  return BSB_OK;
+}
+
 void destroy_env(bsb_env* e) {
-  flush_pending(e);
+  drain_host_steps(e);
   DeviceGuard guard(e->device);
   for (size_t k = 0; k < e->allocs.size(); ++k) { if (e->device >= 0) cudaFree(e->allocs[k]); else free(e->allocs[k]); }
   if (e->device >= 0) {
@@ -269,6 +295,7 @@ void destroy_env(bsb_env* e) {
     if (e->d_obs) cudaFree(e->d_obs);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->order_event) cudaEventDestroy(e->order_event);
+    if (e->fence_event) cudaEventDestroy(e->fence_event);
     if (e->bad_action_host) cudaFreeHost(e->bad_action_host);
     if (e->mailbox) cudaFreeHost(e->mailbox);
     if (e->mail) cudaFree(e->mail);
@@ -418,10 +445,12 @@ int32_t bsb_create(const bsb_config* config, int64_t batch, int32_t device, uint
     e->num_sms = 148;
     if (device >= 0) { int n = 0; if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && n > 0) e->num_sms = n; }
   }
-  e->order_event = nullptr; e->bad_action_host = nullptr; e->bad_action_dev = nullptr;
+  e->order_event = nullptr; e->fence_event = nullptr; e->bad_action_host = nullptr; e->bad_action_dev = nullptr;
   e->mailbox = nullptr; e->mailbox_dev = nullptr; e->mail = nullptr; e->next_ticket = 0; e->pending_ticket = 0;
   { const char* v = getenv("BSB_DOORBELL_TIMEOUT_MS"); const long ms = v ? atol(v) : 200; e->doorbell_timeout_ns = (unsigned long long)(ms > 0 ? ms : 200) * 1000000ull; }
   { const char* v = getenv("BSB_HOST_SPIN"); e->host_spin = v ? (atoi(v) != 0) : 1; }
+  { const char* v = getenv("BSB_HOST_EARLY"); e->host_early = v ? (atoi(v) != 0) : 1; }
+  e->early_inflight = false;
   e->h2d_actions = nullptr; e->d_reward = nullptr; e->d_reward64 = nullptr; e->d_discount = nullptr; e->d_step_type = nullptr; e->d_obs = nullptr;
   e->copy_stream = nullptr;
   DeviceGuard guard(device);
@@ -488,6 +517,14 @@ int32_t bsb_create(const bsb_config* config, int64_t batch, int32_t device, uint
   if (c.family == BSB_MOUNTAIN_CAR) BSB_TRY(env_alloc_t(e, &p.st_f64, 2 * B, true));
   BSB_TRY(env_alloc_t(e, &p.info, (size_t)BSB_MAX_INFO * B, true));
   if (c.flags & BSB_FLAG_TRACK_EPISODES) BSB_TRY(env_alloc_t(e, &p.ep, 5 * B, true));
+  if (c.log_schedule_len > 0) {      // per-lane rows at the Logging wrapper's log-spaced episodes (wrappers.py:140-147)
+    int64_t* sched = nullptr;
+    BSB_TRY(env_alloc_t(e, &sched, (size_t)c.log_schedule_len, false));
+    BSB_TRY(env_upload(e, sched, c.log_schedule, (size_t)c.log_schedule_len * sizeof(int64_t)));
+    p.log_sched = sched; p.n_log_points = (int32_t)c.log_schedule_len;
+    BSB_TRY(env_alloc_t(e, &p.log_rows, (size_t)c.log_schedule_len * (size_t)(5 + e->names.n) * B, true));
+    BSB_TRY(env_alloc_t(e, &p.log_next, B, true));
+  }
   // RNG state
   const bool env_rng = family_uses_env_rng(c);
   const bool noise = c.wrapper == BSB_WRAP_REWARD_NOISE;
@@ -566,7 +603,7 @@ int32_t bsb_steps_done(const bsb_env* env, int64_t* steps) {
 
 int32_t bsb_reset(bsb_env* env, const bsb_outputs* out, void* stream) {
   if (!env || !out || !out->observation) return fail(BSB_INVALID_ARGUMENT, "bsb_reset needs outputs with an observation buffer");
-  { int frc = flush_pending(env); if (frc != BSB_OK) return frc; }
+  { int frc = drain_host_steps(env); if (frc != BSB_OK) return frc; }
   LaunchArgs a = make_args(env, out, nullptr, 1, MODE_RESET);
   int rc = run(env, a, static_cast<cudaStream_t>(stream));
   if (rc == BSB_OK) advance_steps(env, 1);
@@ -575,7 +612,7 @@ int32_t bsb_reset(bsb_env* env, const bsb_outputs* out, void* stream) {
 
 int32_t bsb_step(bsb_env* env, const int32_t* actions, const bsb_outputs* out, void* stream) {
   if (!env || !actions || !out || !out->observation) return fail(BSB_INVALID_ARGUMENT, "bsb_step needs actions and outputs with an observation buffer");
-  { int frc = flush_pending(env); if (frc != BSB_OK) return frc; }
+  { int frc = drain_host_steps(env); if (frc != BSB_OK) return frc; }
   if (env->device < 0) { int vrc = check_host_actions(env, actions, env->p.batch); if (vrc != BSB_OK) return vrc; }
   LaunchArgs a = make_args(env, out, actions, 1, MODE_STEP);
   int rc = run(env, a, static_cast<cudaStream_t>(stream));
@@ -587,7 +624,7 @@ int32_t bsb_rollout(bsb_env* env, int64_t num_steps, const int32_t* actions, uin
                     const bsb_outputs* out, int32_t* actions_out, void* stream) {
   if (!env || !out || !out->observation) return fail(BSB_INVALID_ARGUMENT, "bsb_rollout needs outputs with an observation buffer");
   if (num_steps <= 0) return fail(BSB_INVALID_ARGUMENT, "num_steps must be positive");
-  { int frc = flush_pending(env); if (frc != BSB_OK) return frc; }
+  { int frc = drain_host_steps(env); if (frc != BSB_OK) return frc; }
   if (env->device < 0 && actions) { int vrc = check_host_actions(env, actions, num_steps * env->p.batch); if (vrc != BSB_OK) return vrc; }
   LaunchArgs a = make_args(env, out, actions, num_steps, MODE_STEP);
   a.action_seed = action_seed; a.actions_out = actions_out;
@@ -628,7 +665,7 @@ static int copy_field(bsb_env* env, const double* src, double* dst, void* stream
 int32_t bsb_read_info(bsb_env* env, int32_t index, double* dst, void* stream) {
   if (!env || !dst) return fail(BSB_INVALID_ARGUMENT, "null argument");
   if (index < 0 || index >= env->names.n) return fail(BSB_INVALID_ARGUMENT, "info index out of range");
-  { int frc = flush_pending(env); if (frc != BSB_OK) return frc; }
+  { int frc = drain_host_steps(env); if (frc != BSB_OK) return frc; }
   return copy_field(env, env->p.info + (size_t)index * (size_t)env->p.batch, dst, stream);
 }
 
@@ -636,7 +673,7 @@ int32_t bsb_read_episode_stats(bsb_env* env, int32_t field, double* dst, void* s
   if (!env || !dst) return fail(BSB_INVALID_ARGUMENT, "null argument");
   if (!env->p.ep) return fail(BSB_INVALID_ARGUMENT, "environment was created without BSB_FLAG_TRACK_EPISODES");
   if (field < 0 || field >= 5) return fail(BSB_INVALID_ARGUMENT, "episode-stat field out of range");
-  { int frc = flush_pending(env); if (frc != BSB_OK) return frc; }
+  { int frc = drain_host_steps(env); if (frc != BSB_OK) return frc; }
   const int64_t B = env->p.batch;
   if (env->device >= 0) {
     DeviceGuard guard(env->device);
@@ -652,7 +689,7 @@ int32_t bsb_read_episode_stats(bsb_env* env, int32_t field, double* dst, void* s
 int32_t bsb_sum_episode_stats(bsb_env* env, double* dst5, void* stream) {
   if (!env || !dst5) return fail(BSB_INVALID_ARGUMENT, "null argument");
   if (!env->p.ep) return fail(BSB_INVALID_ARGUMENT, "environment was created without BSB_FLAG_TRACK_EPISODES");
-  { int frc = flush_pending(env); if (frc != BSB_OK) return frc; }
+  { int frc = drain_host_steps(env); if (frc != BSB_OK) return frc; }
   const int64_t B = env->p.batch;
   if (env->device >= 0) {
     DeviceGuard guard(env->device);
@@ -688,13 +725,36 @@ int32_t bsb_sum_episode_stats_many(bsb_env* const* envs, int32_t count, double* 
   SumJobs jobs;
   memset(&jobs, 0, sizeof(jobs));
   for (int32_t k = 0; k < count; ++k) {
-    { int frc = flush_pending(envs[k]); if (frc != BSB_OK) return frc; }
+    { int frc = drain_host_steps(envs[k]); if (frc != BSB_OK) return frc; }
     jobs.job[k].ep = envs[k]->p.ep; jobs.job[k].batch = envs[k]->p.batch; jobs.job[k].calls = envs[k]->steps_done;
     jobs.job[k].clock = envs[k]->graph_safe ? envs[k]->clock : nullptr; jobs.job[k].scratch = envs[k]->sum_scratch;
   }
   episode_sum_many_kernel<<<dim3(kSumBlocks, (unsigned)count), kSumThreads, 0, static_cast<cudaStream_t>(stream)>>>(jobs, dst);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   BSB_CUDA(cudaGetLastError());
+  return BSB_OK;
+}
+
+int32_t bsb_log_layout(const bsb_env* env, int32_t* n_points, int32_t* n_columns) {
+  if (!env || !n_points || !n_columns) return fail(BSB_INVALID_ARGUMENT, "null argument");
+  *n_points = env->p.n_log_points; *n_columns = env->p.log_rows ? 5 + env->names.n : 0;
+  return BSB_OK;
+}
+
+int32_t bsb_read_log_rows(bsb_env* env, double* rows, int32_t* counts, void* stream) {
+  if (!env || !rows || !counts) return fail(BSB_INVALID_ARGUMENT, "null argument");
+  if (!env->p.log_rows) return fail(BSB_INVALID_ARGUMENT, "environment was created without a log schedule");
+  { int frc = drain_host_steps(env); if (frc != BSB_OK) return frc; }
+  const size_t B = (size_t)env->p.batch;
+  const size_t row_bytes = (size_t)env->p.n_log_points * (size_t)(5 + env->names.n) * B * sizeof(double);
+  if (env->device >= 0) {
+    DeviceGuard guard(env->device);
+    BSB_CUDA(cudaMemcpyAsync(rows, env->p.log_rows, row_bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+    BSB_CUDA(cudaMemcpyAsync(counts, env->p.log_next, B * sizeof(int32_t), cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+  } else {
+    memcpy(rows, env->p.log_rows, row_bytes);
+    memcpy(counts, env->p.log_next, B * sizeof(int32_t));
+  }
   return BSB_OK;
 }
 
@@ -710,7 +770,7 @@ int32_t bsb_get_state(bsb_env* env, void* dst_host, int64_t nbytes, void* stream
   if (!env || !dst_host) return fail(BSB_INVALID_ARGUMENT, "null argument");
   bsb_state_bytes(env, &need);
   if (nbytes != need) return fail(BSB_INVALID_ARGUMENT, "state buffer has the wrong size");
-  { int frc = flush_pending(env); if (frc != BSB_OK) return frc; }
+  { int frc = drain_host_steps(env); if (frc != BSB_OK) return frc; }
   DeviceGuard guard(env->device);
   char* dst = static_cast<char*>(dst_host);
   if (env->device >= 0) BSB_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
@@ -730,7 +790,7 @@ int32_t bsb_set_state(bsb_env* env, const void* src_host, int64_t nbytes, void* 
   if (!env || !src_host) return fail(BSB_INVALID_ARGUMENT, "null argument");
   bsb_state_bytes(env, &need);
   if (nbytes != need) return fail(BSB_INVALID_ARGUMENT, "state buffer has the wrong size");
-  { int frc = flush_pending(env); if (frc != BSB_OK) return frc; }
+  { int frc = drain_host_steps(env); if (frc != BSB_OK) return frc; }
   DeviceGuard guard(env->device);
   const char* src = static_cast<const char*>(src_host);
   if (env->device >= 0) BSB_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
@@ -789,7 +849,7 @@ int32_t bsb_step_host(bsb_env* env, const int32_t* actions, const bsb_outputs* h
   if (flags & BSB_HOST_ORDER_AFTER_STREAM) {
     // Work the caller enqueued earlier on ITS stream (bsb_reset / bsb_step / bsb_rollout of this handle) must have
     // finished with the lane state before this step touches it: fence the handle's stream behind it.
-    { int frc = flush_pending(env); if (frc != BSB_OK) return frc; }
+    { int frc = drain_host_steps(env); if (frc != BSB_OK) return frc; }
     if (!env->order_event) BSB_CUDA(cudaEventCreateWithFlags(&env->order_event, cudaEventDisableTiming));
     BSB_CUDA(cudaEventRecord(env->order_event, static_cast<cudaStream_t>(caller_stream)));
     BSB_CUDA(cudaStreamWaitEvent(env->copy_stream, env->order_event, 0));
@@ -833,7 +893,7 @@ int32_t bsb_step_host(bsb_env* env, const int32_t* actions, const bsb_outputs* h
       // observation buffers keep the synchronise.
       const bool spin = env->host_spin && !env->graph_safe && !host_out->observation && f.obs_vec_ok;
       if (!spin) {
-        { int frc = flush_pending(env); if (frc != BSB_OK) return frc; }
+        { int frc = drain_host_steps(env); if (frc != BSB_OK) return frc; }
         bsb_outputs dev;
         dev.observation = f.obs; dev.reward = f.reward; dev.reward_f64 = f.reward_f64; dev.discount = f.discount; dev.step_type = f.step_type;
         int zrc = bsb_step(env, f.actions, &dev, zs);
@@ -858,6 +918,14 @@ int32_t bsb_step_host(bsb_env* env, const int32_t* actions, const bsb_outputs* h
           int lrc = mailbox_launch(env, ticket, env->steps_done, &f, false);
           if (lrc != BSB_OK) return lrc;
         }
+        if ((flags & BSB_HOST_FENCE_CALLER) && env->early_inflight) {
+          // Two-phase step: the observation stores outlive this call.  Fence the caller's stream behind the kernel
+          // (the event is recorded BEFORE the next step's kernel is queued, so it stands for this step only):
+          // whatever the caller enqueues there afterwards sees complete observations.
+          if (!env->fence_event) BSB_CUDA(cudaEventCreateWithFlags(&env->fence_event, cudaEventDisableTiming));
+          BSB_CUDA(cudaEventRecord(env->fence_event, zs));
+          BSB_CUDA(cudaStreamWaitEvent(static_cast<cudaStream_t>(caller_stream), env->fence_event, 0));
+        }
         if (prelaunch) {
           // Queue the NEXT step's kernel now: it becomes resident as this one drains and waits for its doorbell,
           // so the next call pays neither a launch nor a wake-up.  It stands down by itself after
@@ -877,7 +945,7 @@ int32_t bsb_step_host(bsb_env* env, const int32_t* actions, const bsb_outputs* h
       return fail(BSB_INTERNAL, "host step: a freshly launched kernel reported a cancelled doorbell");
     }
   }
-  { int frc = flush_pending(env); if (frc != BSB_OK) return frc; }
+  { int frc = drain_host_steps(env); if (frc != BSB_OK) return frc; }
   if (!env->h2d_actions) BSB_CUDA(cudaMalloc(&env->h2d_actions, B * 4));
   // reward | discount | step_type live in ONE device block so that a caller who keeps its three host arrays
   // back to back (BatchedEnvironment.make_host_buffers does) gets them with a single D2H copy.

@@ -59,6 +59,7 @@ struct bsb_env {
   int32_t* h2d_actions; float* d_reward; double* d_reward64; float* d_discount; int32_t* d_step_type; float* d_obs;
   cudaStream_t copy_stream;
   cudaEvent_t order_event;            // BSB_HOST_ORDER_AFTER_STREAM: fences copy_stream behind the caller's stream
+  cudaEvent_t fence_event;            // BSB_HOST_FENCE_CALLER: fences the caller's stream behind a two-phase host step
   // Out-of-range actions: the kernels clamp them before any table index or state packing and raise
   // this pinned flag; bsb_step_host / bsb_invalid_actions report it.
   int32_t* bad_action_host; int32_t* bad_action_dev;
@@ -70,6 +71,8 @@ struct bsb_env {
   unsigned long long pending_ticket;  // pre-launched launch waiting for its doorbell (0 = none); it is for step steps_done
   unsigned long long doorbell_timeout_ns;
   int host_spin;                      // BSB_HOST_SPIN (default 1): completion through the mailbox instead of a synchronise
+  int host_early;                     // BSB_HOST_EARLY (default 1): two-phase host steps (scalars first) where the family allows
+  bool early_inflight;                // a two-phase host step may still be streaming observations on copy_stream
 };
 
 namespace bsb {

@@ -52,6 +52,12 @@ struct EnvParams {
   double* st_f64;      // [6][B] float64 dynamics state (+ episode_return)
   double* info;        // [BSB_MAX_INFO][B] bsuite_info() accumulators
   double* ep;          // [5][B] Logging accumulators, or null
+  // Log-spaced rows of the Logging wrapper (wrappers.py:99-110, 140-147), recorded per lane on the device:
+  // row k of lane i = the wrapper's columns at the LAST timestep that made episode == log_sched[k].
+  double* log_rows;          // [n_log_points][5 + n_info][B], or null
+  const int64_t* log_sched;  // [n_log_points] ascending episode counts at which the reference writes a row
+  int32_t* log_next;         // [B] rows recorded so far (= index of the next schedule entry)
+  int32_t n_log_points, pad_log;
   // RNG state: env stream and reward-wrapper stream
   uint64_t* rng_pos;  double* rng_gauss;
   uint64_t* wrng_pos; double* wrng_gauss;
@@ -563,6 +569,25 @@ struct EpisodeStats {
 };
 
 // Column `field` (0 steps, 1 episode, 2 total_return, 3 episode_len, 4 episode_return) of lane i after `calls` calls.
+BSB_HD double episode_stat(const EnvParams& p, int64_t i, int field, int64_t calls);
+
+// Does the LAST timestep lane i has just produced fall on the log schedule?  (`episode` already counts it.)
+BSB_HD bool log_row_due(const EnvParams& p, int64_t i) {
+  const int32_t k = p.log_next[i];
+  return k < p.n_log_points && (int64_t)p.ep[p.batch + i] == p.log_sched[k];
+}
+// Records the row: the five Logging columns and bsuite_info() exactly as the reference's `_log_bsuite_data`
+// (wrappers.py:113-125) reads them right after the LAST timestep.  The lane's state, accumulators and info fields
+// must have been stored to memory (F::store, EpisodeStats::store) before the call.
+BSB_HD void log_row_write(const EnvParams& p, int64_t i, int64_t calls) {
+  const int32_t k = p.log_next[i];
+  const int64_t cols = 5 + p.n_info;
+  double* row = p.log_rows + ((int64_t)k * cols) * p.batch + i;
+  for (int f = 0; f < 5; ++f) row[(int64_t)f * p.batch] = episode_stat(p, i, f, calls);
+  for (int f = 0; f < p.n_info; ++f) row[(int64_t)(5 + f) * p.batch] = p.info[(int64_t)f * p.batch + i];
+  p.log_next[i] = k + 1;
+}
+
 BSB_HD double episode_stat(const EnvParams& p, int64_t i, int field, int64_t calls) {
   const int64_t B = p.batch;
   switch (field) {

@@ -70,6 +70,7 @@ struct LaunchArgs {
                                      // paying a stream synchronise.
   struct DeviceMail* mail;           // device memory: doorbell relay + finished-CTA counter
   unsigned long long ticket;
+  int32_t early_scalars;             // 1: two-phase host step -- signal the host when the scalars of every lane are out
   int32_t wait_doorbell;             // 1: pre-launched -- poll the doorbell for `ticket`, then take the buffers from the mailbox
   unsigned long long doorbell_timeout_ns;
   int32_t* bad_action;      // pinned host flag (device alias): set to 1 when an action is outside [0, num_actions)
@@ -85,13 +86,16 @@ struct MailFields {
   int32_t obs_vec_ok, pad;
 };
 struct HostMailbox {
-  volatile unsigned long long doorbell; unsigned long long pad0[7];     // own 64-byte line
-  MailFields in;                          unsigned long long pad1[1];
-  volatile unsigned long long done;     unsigned long long pad2[7];
+  volatile unsigned long long doorbell;   // host -> device, word 0 of the line the device polls
+  MailFields in;                          // words 1..7 of the same 64-byte line
+  unsigned long long pad0[8];
+  volatile unsigned long long done;     unsigned long long pad1[7];     // device -> host, a line of its own
 };
+static_assert(sizeof(MailFields) == 56, "doorbell + fields must fill exactly one 64-byte line");
 struct DeviceMail {
   volatile unsigned long long relay;      // ticket (| MAIL_CANCEL) most recently taken from the host doorbell
-  unsigned long long finished;            // blocks of the current launch that have finished
+  unsigned long long finished;            // blocks of the current launch that have finished (phase 1, if two-phase)
+  volatile unsigned long long phase1;     // ticket of the latest two-phase launch whose phase 1 is complete
   MailFields in;                          // the host's fields, copied once per launch by block 0
 };
 
@@ -152,6 +156,11 @@ BSB_HD StepOut lane_transition(const EnvParams& p, int64_t i, typename F::Lane& 
 
 // Observation emitter of each family.
 static const int EMIT_ROWS = 0, EMIT_ONEHOT = 1, EMIT_TWOHOT = 2, EMIT_IMAGE = 3;
+// Families whose observation is a pure function of the STORED lane state (F::describe after F::load): their
+// host-driven steps can deliver the scalars before the observation is streamed (two-phase host step).
+template <class F> struct ObsFromState { static const bool value = false; };
+template <> struct ObsFromState<DeepSea> { static const bool value = true; };
+template <> struct ObsFromState<Catch> { static const bool value = true; };
 template <class F> struct EmitKind { static const int value = EMIT_ROWS; };
 template <> struct EmitKind<DeepSea> { static const int value = EMIT_ONEHOT; };
 template <> struct EmitKind<Catch> { static const int value = EMIT_TWOHOT; };
@@ -520,23 +529,30 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
   io.discount = a.discount; io.step_type = a.step_type; io.obs_vec_ok = a.obs_vec_ok; io.pad = 0;
   bool cancelled = false;
   if (a.mailbox && a.wait_doorbell) {
+    if (blockIdx.x == 0 && warp == 0) {
+      // The one poller of host memory: lanes 0..7 read the mailbox's first 64-byte line (doorbell + fields) with ONE
+      // coalesced request per poll; when the ring shows, the line is read once more (the host wrote the fields
+      // before the doorbell, so this second read cannot be stale), parked in device memory, and the ticket is
+      // relayed to the other blocks through L2.
+      const volatile unsigned long long* line = &a.mailbox->doorbell;
+      const unsigned long long deadline = global_timer_ns() + a.doorbell_timeout_ns;
+      unsigned long long word = 0, seen;
+      do {
+        if (tid < 8) word = ld_sys_u64(line + tid);
+        seen = __shfl_sync(0xffffffffu, word, 0);
+      } while ((seen & ~MAIL_CANCEL) < a.ticket && global_timer_ns() < deadline);
+      if ((seen & ~MAIL_CANCEL) < a.ticket) seen = a.ticket | MAIL_CANCEL;        // nobody rang: stand down
+      __threadfence_system();
+      if (tid < 8) word = ld_sys_u64(line + tid);
+      if (tid >= 1 && tid < 8) reinterpret_cast<unsigned long long*>(&a.mail->in)[tid - 1] = word;
+      __threadfence();
+      __syncwarp();
+      if (tid == 0) a.mail->relay = seen;
+    }
     if (threadIdx.x == 0) {
       unsigned long long seen;
-      if (blockIdx.x == 0) {                 // the one poller of host memory
-        const unsigned long long deadline = global_timer_ns() + a.doorbell_timeout_ns;
-        do { seen = ld_sys_u64(&a.mailbox->doorbell); }
-        while ((seen & ~MAIL_CANCEL) < a.ticket && global_timer_ns() < deadline);
-        if ((seen & ~MAIL_CANCEL) < a.ticket) seen = a.ticket | MAIL_CANCEL;      // nobody rang: stand down
-        __threadfence_system();              // the fields were written before the doorbell
-        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&a.mailbox->in);
-        unsigned long long* dst = reinterpret_cast<unsigned long long*>(&a.mail->in);
-        for (int k = 0; k < (int)(sizeof(MailFields) / 8); ++k) dst[k] = ld_sys_u64(src + k);
-        __threadfence();
-        a.mail->relay = seen;
-      } else {
-        do { seen = a.mail->relay; } while ((seen & ~MAIL_CANCEL) < a.ticket);
-        __threadfence();
-      }
+      do { seen = a.mail->relay; } while ((seen & ~MAIL_CANCEL) < a.ticket);
+      __threadfence();
       mail_cancel = (seen & MAIL_CANCEL) ? 1 : 0;
       const volatile unsigned long long* src = reinterpret_cast<const volatile unsigned long long*>(&a.mail->in);
       unsigned long long* dst = reinterpret_cast<unsigned long long*>(&mail_in);
@@ -575,6 +591,178 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
   unsigned emitted = 0;          // bulk stores issued by this warp so far (double-buffer parity)
   bool any_bulk = false;
 
+  // Observation emitter of this warp for one chunk and step (shared by the ordinary loop and by the two-phase
+  // host-step path below); the staging state above persists across calls.
+  auto emit_obs = [&](const typename F::Lane& L, R& rng, float* obs_t, int64_t warp_base, int n_lanes, int64_t lane,
+                      bool active, bool bulk) {
+    if (kEmit == EMIT_ONEHOT) {
+      const int hot = Descriptor<F>::a(L);
+      if (bulk) {
+        // Groups of m consecutive lanes share one staging buffer (m tiles, contiguous in global memory too) and
+        // leave as ONE bulk store of up to m * 4K bytes: large stores amortise the per-operation cost of the
+        // TMA unit (measured: ~70 ns + bytes / 64 GB/s per SM).
+        const int m = a.group_lanes;
+        for (int g0 = 0; g0 < n_lanes; g0 += m) {
+          const int in_group = (n_lanes - g0) < m ? (n_lanes - g0) : m;
+          const int s = (int)(emitted & 1u);
+          float* group = stage + (size_t)s * m * K;
+          if (tid == 0) bulk_wait_read<TILE_STAGES - 1>();    // the store two back, last reader of `group`, is done
+          __syncwarp();
+          if (s == 0) { if (tile_poked0 >= 0) { group[tile_poked0] = 0.f; tile_poked0 = -1; } }
+          else        { if (tile_poked1 >= 0) { group[tile_poked1] = 0.f; tile_poked1 = -1; } }
+          __syncwarp();     // a thread of an earlier group may clear the very cell another thread sets now
+          if (tid >= g0 && tid < g0 + in_group && hot >= 0) {
+            const int cell = (tid - g0) * K + hot;
+            group[cell] = 1.f;
+            if (s == 0) tile_poked0 = cell; else tile_poked1 = cell;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (tid == 0) {
+            float* tile_dst = obs_t + (warp_base + g0) * (int64_t)K;
+            const uint32_t tile_bytes = (uint32_t)in_group * (uint32_t)K * 4u;
+            bulk_store_obs(tile_dst, group, tile_bytes, a.l2_hint);
+            bulk_commit();
+          }
+          ++emitted;
+        }
+      } else {
+        emit_onehot_vec(obs_t, warp_base, n_lanes, K, hot, vec && (K & 3) == 0);
+      }
+    } else if (kEmit == EMIT_TWOHOT) {
+      const int hot_a = Descriptor<F>::a(L), hot_b = Descriptor<F>::b(L);
+      if (bulk) {
+        const int buf = (int)(emitted & row_mask);
+        float* boards = stage + (size_t)buf * 32 * K;
+        if (tid == 0) { if (row_mask) bulk_wait_read<1>(); else bulk_wait_read<0>(); }   // the store that last read `boards` is done with it
+        __syncwarp();
+        float* mine = boards + tid * K;
+        const int old_a = buf ? poked_a1 : poked_a0, old_b = buf ? poked_b1 : poked_b0;
+        if (old_a >= 0) mine[old_a] = 0.f;
+        if (old_b >= 0) mine[old_b] = 0.f;
+        int new_a = -1, new_b = -1;
+        if (active) { mine[hot_a] = 1.f; mine[hot_b] = 1.f; new_a = hot_a; new_b = hot_b; }
+        if (buf) { poked_a1 = new_a; poked_b1 = new_b; } else { poked_a0 = new_a; poked_b0 = new_b; }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (tid == 0) { bulk_store_obs(obs_t + warp_base * (int64_t)K, boards, (uint32_t)n_lanes * (uint32_t)K * 4u, a.l2_hint); bulk_commit(); }
+        ++emitted;
+      } else {
+        emit_twohot_vec(obs_t, warp_base, n_lanes, K, hot_a, hot_b, vec);
+      }
+    } else if (kEmit == EMIT_IMAGE) {
+      const int image = Descriptor<F>::a(L);
+      if (bulk) emit_image_bulk(p, stage, cta_zero, obs_t, warp_base, n_lanes, K, active ? image : -1, a.group_lanes, a.l2_hint, emitted);
+      else emit_image(p, stage, obs_t, warp_base, n_lanes, K, image, vec && (K & 3) == 0);
+    } else if (!a.stage_rows) {
+      // observation rows too long for a shared-memory stage: every thread renders its row in place
+      if (active) RowRenderer<F, R>::run(p, L, rng, obs_t + lane * (int64_t)K);
+    } else {
+      float* rows = stage + (size_t)(emitted & row_mask) * 32 * K;
+      if (bulk) { if (tid == 0) { if (row_mask) bulk_wait_read<1>(); else bulk_wait_read<0>(); } }
+      __syncwarp();
+      if (active) RowRenderer<F, R>::run(p, L, rng, rows + tid * K);
+      if (bulk) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (tid == 0) { bulk_store_obs(obs_t + warp_base * (int64_t)K, rows, (uint32_t)n_lanes * (uint32_t)K * 4u, a.l2_hint); bulk_commit(); }
+      } else {
+        __syncwarp();
+        flush_rows_vec(rows, obs_t, warp_base, n_lanes, K, vec);
+      }
+      ++emitted;
+    }
+  };
+  // Which chunks leave through the TMA unit (16-byte aligned spans); warp-uniform per chunk.
+  auto chunk_is_bulk = [&](int n_lanes) -> bool {
+    bool bulk = a.emit_bulk && vec;
+    if (kEmit == EMIT_ROWS) bulk = bulk && K >= 3 && ((n_lanes * K) & 3) == 0;
+    if (kEmit == EMIT_TWOHOT) bulk = bulk && ((n_lanes * K) & 3) == 0;
+    if (kEmit == EMIT_ONEHOT) bulk = bulk && ((K & 3) == 0 || ((n_lanes % a.group_lanes) == 0 && ((a.group_lanes * K) & 3) == 0));
+    if (kEmit == EMIT_IMAGE) bulk = bulk && (K & 3) == 0;
+    return bulk;
+  };
+
+  // ---- two-phase host step (a.early_scalars; families whose observation is a function of the stored state) ----
+  // A host-driven step (bsb_step_host) returns when reward / discount / step_type are in host memory; the
+  // observation stays on the device.  So the transitions of ALL chunks run first (phase 1: a few microseconds,
+  // statically dealt), the host is signalled, and the observations are streamed afterwards (phase 2, dynamically
+  // dealt as usual) while the host already decides the next action.  Phase 2 re-reads the lane state phase 1
+  // stored (L2-resident) and renders from it; a warp's first chunk stays in registers.
+  if constexpr (ObsFromState<F>::value) {
+    if (a.early_scalars && a.mailbox && !cancelled) {
+      const int64_t own = (int64_t)blockIdx.x * warps_per_cta + warp;
+      typename F::Lane keep;
+      F::init(p, keep);
+      for (int64_t c = own; c < n_chunks; c += total_warps) {
+        const int64_t warp_base = c * cl;
+        const int n_lanes = (B - warp_base) < cl ? (int)(B - warp_base) : cl;
+        const int64_t lane = warp_base + tid;
+        typename F::Lane L;
+        F::init(p, L);
+        if (tid < n_lanes) {
+          R rng, wrng;
+          EpisodeStats ep;
+          F::load(p, lane, L);
+          if (has_rng) rng_open(rng, p, lane, false);
+          if (kNoise) rng_open(wrng, p, lane, true);
+          if (kTrack) ep.load(p, lane);
+          int32_t action = __ldcv(io.actions + lane);
+          if ((uint32_t)action >= (uint32_t)p.num_actions) {
+            if (a.bad_action) *a.bad_action = 1;
+            action = action < 0 ? 0 : p.num_actions - 1;
+          }
+          const bool after_last = L.nr != 0;
+          const StepOut o = lane_transition<F, R, R>(p, lane, L, rng, wrng, action, MODE_STEP, kNoise);
+          F::store(p, lane, L);
+          if (has_rng) rng_close(rng, p, lane, false);
+          if (kNoise) rng_close(wrng, p, lane, true);
+          if (kTrack) {
+            ep.track(p, lane, o, step0, after_last);
+            ep.store(p, lane);
+            if (p.log_rows && o.step_type == LAST && log_row_due(p, lane)) log_row_write(p, lane, step0 + 1);
+          }
+          if (io.reward) io.reward[lane] = (float)o.reward;
+          if (io.reward_f64) io.reward_f64[lane] = o.reward;
+          if (io.discount) io.discount[lane] = o.discount;
+          if (io.step_type) io.step_type[lane] = o.step_type;
+        }
+        if (c == own) keep = L;
+      }
+      __threadfence_system();                // scalars (host memory) and lane state (device memory) are out ...
+      __syncthreads();
+      if (threadIdx.x == 0 && atomicAdd(&a.mail->finished, 1ull) == (unsigned long long)gridDim.x - 1ull) {
+        a.mail->finished = 0ull;
+        a.mail->phase1 = a.ticket;           // ... for every chunk: phase 2 may read any lane's state now
+        __threadfence_system();
+        st_sys_u64(&a.mailbox->done, a.ticket);      // and the host may read its scalars
+      }
+      bool mine = true;
+      int64_t c = own;
+      while (c < n_chunks) {
+        const int64_t warp_base = c * cl;
+        const int n_lanes = (B - warp_base) < cl ? (int)(B - warp_base) : cl;
+        const int64_t lane = warp_base + tid;
+        const bool active = tid < n_lanes;
+        typename F::Lane L = keep;
+        if (!mine) {
+          // a dynamically dealt chunk: some other warp ran its phase 1 -- long ago in practice, but wait for it
+          if (tid == 0) while (a.mail->phase1 != a.ticket) {}
+          __syncwarp();
+          F::init(p, L);
+          if (active) { F::load(p, lane, L); F::describe(p, L); }
+        }
+        const bool bulk = chunk_is_bulk(n_lanes);
+        any_bulk = any_bulk || bulk;
+        R unused_rng;
+        emit_obs(L, unused_rng, io.obs, warp_base, n_lanes, lane, active, bulk);
+        mine = false;
+        c = dynamic ? fetch_chunk() : n_chunks;
+      }
+      cur_chunk = n_chunks;                  // nothing left for the ordinary loop
+    }
+  }
+
   while (cur_chunk < n_chunks) {
     const int64_t warp_base = cur_chunk * cl;
     // eager policy: reserve the next chunk now; lazy (default): only after this chunk's stores are issued
@@ -582,12 +770,7 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
     const int n_lanes = (B - warp_base) < cl ? (int)(B - warp_base) : cl;
     const int64_t lane = warp_base + tid;
     const bool active = tid < n_lanes;
-    // Bulk (TMA) emission needs 16-byte aligned spans; the choice is warp-uniform per chunk.
-    bool bulk = a.emit_bulk && vec;
-    if (kEmit == EMIT_ROWS) bulk = bulk && K >= 3 && ((n_lanes * K) & 3) == 0;
-    if (kEmit == EMIT_TWOHOT) bulk = bulk && ((n_lanes * K) & 3) == 0;
-    if (kEmit == EMIT_ONEHOT) bulk = bulk && ((K & 3) == 0 || ((n_lanes % a.group_lanes) == 0 && ((a.group_lanes * K) & 3) == 0));
-    if (kEmit == EMIT_IMAGE) bulk = bulk && (K & 3) == 0;
+    const bool bulk = chunk_is_bulk(n_lanes);
     any_bulk = any_bulk || bulk;
 
     typename F::Lane L;
@@ -633,7 +816,13 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
         }
         const bool after_last = L.nr != 0;
         const StepOut o = lane_transition<F, R, R>(p, lane, L, rng, wrng, action, a.mode, kNoise);
-        if (kTrack) ep.track(p, lane, o, step0 + t, after_last);
+        if (kTrack) {
+          ep.track(p, lane, o, step0 + t, after_last);
+          if (p.log_rows && o.step_type == LAST && log_row_due(p, lane)) {      // <= 49 times per 10 000 episodes
+            F::store(p, lane, L); ep.store(p, lane);
+            log_row_write(p, lane, step0 + t + 1);
+          }
+        }
         if (io.reward) io.reward[off] = (float)o.reward;
         if (io.reward_f64) io.reward_f64[off] = o.reward;
         if (io.discount) io.discount[off] = o.discount;
@@ -641,83 +830,7 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
       }
       float* obs_t = io.obs + t * B * (int64_t)K;
 
-      if (kEmit == EMIT_ONEHOT) {
-        const int hot = Descriptor<F>::a(L);
-        if (bulk) {
-          // Groups of m consecutive lanes share one staging buffer (m tiles, contiguous in global memory too) and
-          // leave as ONE bulk store of up to m * 4K bytes: large stores amortise the per-operation cost of the
-          // TMA unit (measured: ~70 ns + bytes / 64 GB/s per SM).
-          const int m = a.group_lanes;
-          for (int g0 = 0; g0 < n_lanes; g0 += m) {
-            const int in_group = (n_lanes - g0) < m ? (n_lanes - g0) : m;
-            const int s = (int)(emitted & 1u);
-            float* group = stage + (size_t)s * m * K;
-            if (tid == 0) bulk_wait_read<TILE_STAGES - 1>();    // the store two back, last reader of `group`, is done
-            __syncwarp();
-            if (s == 0) { if (tile_poked0 >= 0) { group[tile_poked0] = 0.f; tile_poked0 = -1; } }
-            else        { if (tile_poked1 >= 0) { group[tile_poked1] = 0.f; tile_poked1 = -1; } }
-            __syncwarp();     // a thread of an earlier group may clear the very cell another thread sets now
-            if (tid >= g0 && tid < g0 + in_group && hot >= 0) {
-              const int cell = (tid - g0) * K + hot;
-              group[cell] = 1.f;
-              if (s == 0) tile_poked0 = cell; else tile_poked1 = cell;
-            }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (tid == 0) {
-              float* tile_dst = obs_t + (warp_base + g0) * (int64_t)K;
-              const uint32_t tile_bytes = (uint32_t)in_group * (uint32_t)K * 4u;
-              bulk_store_obs(tile_dst, group, tile_bytes, a.l2_hint);
-              bulk_commit();
-            }
-            ++emitted;
-          }
-        } else {
-          emit_onehot_vec(obs_t, warp_base, n_lanes, K, hot, vec && (K & 3) == 0);
-        }
-      } else if (kEmit == EMIT_TWOHOT) {
-        const int hot_a = Descriptor<F>::a(L), hot_b = Descriptor<F>::b(L);
-        if (bulk) {
-          const int buf = (int)(emitted & row_mask);
-          float* boards = stage + (size_t)buf * 32 * K;
-          if (tid == 0) { if (row_mask) bulk_wait_read<1>(); else bulk_wait_read<0>(); }   // the store that last read `boards` is done with it
-          __syncwarp();
-          float* mine = boards + tid * K;
-          const int old_a = buf ? poked_a1 : poked_a0, old_b = buf ? poked_b1 : poked_b0;
-          if (old_a >= 0) mine[old_a] = 0.f;
-          if (old_b >= 0) mine[old_b] = 0.f;
-          int new_a = -1, new_b = -1;
-          if (active) { mine[hot_a] = 1.f; mine[hot_b] = 1.f; new_a = hot_a; new_b = hot_b; }
-          if (buf) { poked_a1 = new_a; poked_b1 = new_b; } else { poked_a0 = new_a; poked_b0 = new_b; }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (tid == 0) { bulk_store_obs(obs_t + warp_base * (int64_t)K, boards, (uint32_t)n_lanes * (uint32_t)K * 4u, a.l2_hint); bulk_commit(); }
-          ++emitted;
-        } else {
-          emit_twohot_vec(obs_t, warp_base, n_lanes, K, hot_a, hot_b, vec);
-        }
-      } else if (kEmit == EMIT_IMAGE) {
-        const int image = Descriptor<F>::a(L);
-        if (bulk) emit_image_bulk(p, stage, cta_zero, obs_t, warp_base, n_lanes, K, active ? image : -1, a.group_lanes, a.l2_hint, emitted);
-        else emit_image(p, stage, obs_t, warp_base, n_lanes, K, image, vec && (K & 3) == 0);
-      } else if (!a.stage_rows) {
-        // observation rows too long for a shared-memory stage: every thread renders its row in place
-        if (active) RowRenderer<F, R>::run(p, L, rng, obs_t + lane * (int64_t)K);
-      } else {
-        float* rows = stage + (size_t)(emitted & row_mask) * 32 * K;
-        if (bulk) { if (tid == 0) { if (row_mask) bulk_wait_read<1>(); else bulk_wait_read<0>(); } }
-        __syncwarp();
-        if (active) RowRenderer<F, R>::run(p, L, rng, rows + tid * K);
-        if (bulk) {
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (tid == 0) { bulk_store_obs(obs_t + warp_base * (int64_t)K, rows, (uint32_t)n_lanes * (uint32_t)K * 4u, a.l2_hint); bulk_commit(); }
-        } else {
-          __syncwarp();
-          flush_rows_vec(rows, obs_t, warp_base, n_lanes, K, vec);
-        }
-        ++emitted;
-      }
+      emit_obs(L, rng, obs_t, warp_base, n_lanes, lane, active, bulk);
     }
 
     if (active) {
@@ -731,9 +844,10 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
   if (any_bulk && tid == 0) {
     // shared memory must outlive the last bulk read; in doorbell mode the host takes `done` to mean that the
     // observations are in device memory, so there the stores themselves must have completed
-    if (a.mailbox) bulk_wait_all(); else bulk_wait_read<0>();
+    if (a.mailbox && !a.early_scalars) bulk_wait_all(); else bulk_wait_read<0>();
   }
-  if (a.mailbox) {
+  const bool signalled_early = ObsFromState<F>::value && a.early_scalars && !cancelled;
+  if (a.mailbox && !signalled_early) {
     __threadfence_system();                  // every thread: its zero-copy outputs are visible to the host ...
     __syncthreads();                         // ... before the CTA counts itself finished
     if (threadIdx.x == 0) {

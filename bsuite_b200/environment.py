@@ -50,7 +50,7 @@ def _resolve_device(device) -> int:
   return dev.index if dev.index is not None else torch.cuda.current_device()
 
 
-def _make_config(spec: EnvSpec, rng_kind: int, flags: int):
+def _make_config(spec: EnvSpec, rng_kind: int, flags: int, log_schedule=None):
   cfg = _lib.Config()
   cfg.family = spec.family
   cfg.wrapper = spec.wrapper
@@ -71,6 +71,11 @@ def _make_config(spec: EnvSpec, rng_kind: int, flags: int):
     cfg.table2 = table2.ctypes.data
     cfg.table2_bytes = table2.nbytes
     keep.append(table2)
+  if log_schedule is not None and len(log_schedule):
+    schedule = np.ascontiguousarray(log_schedule, dtype=np.int64)
+    cfg.log_schedule = schedule.ctypes.data
+    cfg.log_schedule_len = schedule.size
+    keep.append(schedule)
   return cfg, keep
 
 
@@ -78,9 +83,9 @@ class _Handle:
   """Owns one bsb_env*."""
 
   def __init__(self, spec: EnvSpec, batch: int, device_ordinal: int, seed: int, lane_offset: int,
-               rng_kind: int, flags: int):
+               rng_kind: int, flags: int, log_schedule=None):
     self.lib = _lib.load()
-    cfg, keep = _make_config(spec, rng_kind, flags)
+    cfg, keep = _make_config(spec, rng_kind, flags, log_schedule)
     ptr = ctypes.c_void_p()
     _lib.check(self.lib.bsb_create(ctypes.byref(cfg), batch, device_ordinal, seed & _MASK64,
                                    lane_offset & _MASK64, ctypes.byref(ptr)))
@@ -163,7 +168,7 @@ class BatchedEnvironment:
 
   def __init__(self, spec: EnvSpec, batch: int, device='cuda', seed: Optional[int] = None,
                rng: str = 'philox', lane_offset: int = 0, track_episodes: bool = False,
-               reward_dtype='float32'):
+               reward_dtype='float32', record_rows: bool = False):
     import torch
     self._torch = torch
     self._spec = spec
@@ -181,10 +186,18 @@ class BatchedEnvironment:
       raise ValueError('Seed must be between 0 and 2**32 - 1')   # numpy's own message
     self._lane_offset = int(lane_offset)
     self._async_work = False        # something was enqueued on a torch stream since the last host-driven step
+    # record_rows: every lane keeps the rows the reference's Logging wrapper would have written for it, at the
+    # log-spaced episode counts of utils/wrappers.py:140-147 (recording.write_lane_csvs turns them into files)
+    track_episodes = bool(track_episodes or record_rows)
     flags = _lib.FLAG_TRACK_EPISODES if track_episodes else 0
     self._track = bool(track_episodes)
+    self._log_schedule = None
+    if record_rows:
+      from bsuite_b200 import recording  # pylint: disable=import-outside-toplevel
+      self._log_schedule = recording.log_schedule(spec.bsuite_num_episodes)
     self._reward_dtype = torch.float64 if str(reward_dtype).endswith('64') else torch.float32
-    self._handle = _Handle(spec, self._batch, self._ordinal, self._seed, self._lane_offset, self._rng_kind, flags)
+    self._handle = _Handle(spec, self._batch, self._ordinal, self._seed, self._lane_offset, self._rng_kind, flags,
+                           self._log_schedule)
     self._lib = self._handle.lib
     n = ctypes.c_int32()
     _lib.check(self._lib.bsb_info_count(self._handle.ptr, ctypes.byref(n)))
@@ -335,10 +348,14 @@ class BatchedEnvironment:
       houts.observation = out.observation.data_ptr()
     flags = _lib.HOST_PRELAUNCH if prelaunch else 0
     stream = None
-    if self._async_work and self._ordinal >= 0:
-      flags |= _lib.HOST_ORDER_AFTER_STREAM
+    if self._ordinal >= 0:
+      # fence torch's current stream behind the step: deep_sea / catch return as soon as the scalars have landed
+      # (two-phase host step), the observation is complete for whatever is enqueued on this stream afterwards
+      flags |= _lib.HOST_FENCE_CALLER
       stream = self._stream()
-      self._async_work = False
+      if self._async_work:
+        flags |= _lib.HOST_ORDER_AFTER_STREAM
+        self._async_work = False
     status = self._lib.bsb_step_host(self._handle.ptr, actions.data_ptr(), ctypes.byref(houts), dev_obs, stream, flags)
     if status:
       _lib.check(status)
@@ -449,6 +466,21 @@ class BatchedEnvironment:
       _lib.check(self._lib.bsb_read_episode_stats(self._handle.ptr, k, ctypes.c_void_p(dst.data_ptr()), self._stream()))
       result[name] = dst
     return result
+
+  def logged_rows(self) -> Dict[str, Any]:
+    """The per-lane log rows recorded on the device (`record_rows=True`): `columns` (the reference wrapper's five
+    columns + the bsuite_info() keys), `rows` float64 [n_points, n_columns, B], `counts` int32 [B] (rows recorded
+    so far per lane) and `schedule` (episode count of every row index)."""
+    if self._log_schedule is None:
+      raise RuntimeError('create the environment with record_rows=True')
+    torch = self._torch
+    n_points, n_cols = ctypes.c_int32(), ctypes.c_int32()
+    _lib.check(self._lib.bsb_log_layout(self._handle.ptr, ctypes.byref(n_points), ctypes.byref(n_cols)))
+    rows = torch.empty((n_points.value, n_cols.value, self._batch), dtype=torch.float64, device=self._device)
+    counts = torch.empty(self._batch, dtype=torch.int32, device=self._device)
+    _lib.check(self._lib.bsb_read_log_rows(self._handle.ptr, rows.data_ptr(), counts.data_ptr(), self._stream()))
+    return dict(columns=_lib.EPISODE_STAT_FIELDS + self._info_names, rows=rows, counts=counts,
+                schedule=np.asarray(self._log_schedule))
 
   def episode_stat_sums(self, out=None):
     """Sums over this environment's lanes of (steps, episode, total_return, episode_len, episode_return): a float64

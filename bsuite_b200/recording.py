@@ -31,6 +31,47 @@ def is_log_point(count: int, ratios: Optional[Sequence[float]] = None) -> bool:
   return any(count == 10**exponent * ratio for ratio in ratios)
 
 
+def log_schedule(num_episodes: int) -> 'list[int]':
+  """The episode counts in [1, num_episodes] at which the reference's Logging wrapper writes a row."""
+  return [e for e in range(1, int(num_episodes) + 1) if is_log_point(e)]
+
+
+_INT_COLUMNS = frozenset(['steps', 'episode', 'episode_len', 'total_bad_episodes', 'total_perfect'])
+
+
+def write_lane_csvs(env, bsuite_id: str, results_root: str, lanes: Optional[Sequence[int]] = None,
+                    overwrite: bool = False) -> 'list[str]':
+  """Writes the rows a `record_rows=True` batched environment has recorded, one results directory per lane.
+
+  Every lane is an independent run of `bsuite_id` (its own seed), so each gets what the reference's
+  `load_and_record_to_csv` would have produced for it: `<results_root>/lane_<global lane>/bsuite_id_-_<name>-<i>.csv`
+  (logging/csv_logging.py:29-31, 73-89), one row per log point with the columns `steps, episode, total_return,
+  episode_len, episode_return` + the `bsuite_info()` keys.  Each directory loads with the reference's
+  `csv_load.load_one_result_set` / `load_bsuite` (csv_load.py:29-57).  Returns the directories written.
+  """
+  logged = env.logged_rows()
+  columns = list(logged['columns'])
+  rows = logged['rows'].cpu().numpy()              # [n_points, n_columns, B]
+  counts = logged['counts'].cpu().numpy()
+  lanes = range(env.batch) if lanes is None else lanes
+  filename = f"{BSUITE_PREFIX}{bsuite_id.replace('/', SAFE_SEPARATOR)}.csv"
+  written = []
+  for lane in lanes:
+    directory = os.path.join(results_root, f'lane_{env.lane_offset + lane:07d}')
+    os.makedirs(directory, exist_ok=True)
+    path = os.path.join(directory, filename)
+    if os.path.exists(path) and not overwrite:
+      raise ValueError(f'File {path} already exists. Specify a different directory, or set overwrite=True '
+                       'to overwrite existing data.')
+    with open(path, 'w', newline='') as fh:
+      writer = csv.writer(fh)
+      writer.writerow(columns)
+      for k in range(int(counts[lane])):
+        writer.writerow([int(v) if c in _INT_COLUMNS else float(v) for c, v in zip(columns, rows[k, :, lane])])
+    written.append(directory)
+  return written
+
+
 class CsvLogger:
   """Appends rows to `<results_dir>/bsuite_id_-_<name>-<i>.csv` (csv_logging.py:29-31, 73-80)."""
 

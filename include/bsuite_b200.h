@@ -133,6 +133,15 @@ typedef struct bsb_config {
   /*   mnist    : uint8  [num_data] labels */
   const void* table2;
   int64_t table2_bytes;
+
+  /* Log schedule of the reference's Logging wrapper (utils/wrappers.py:99-110,
+   * 140-147): the ascending episode counts {1, 1.2, ..., 10} x 10^k up to
+   * bsuite_num_episodes at which it writes a row.  When given (host int64
+   * array; needs BSB_FLAG_TRACK_EPISODES) every lane records its own row --
+   * the five Logging columns + bsuite_info() at that LAST timestep -- on the
+   * device (bsb_read_log_rows).  NULL / 0: no rows are recorded. */
+  const int64_t* log_schedule;
+  int64_t log_schedule_len;
 } bsb_config;
 
 /* bsb_config.flags */
@@ -259,6 +268,18 @@ int32_t bsb_sum_episode_stats(bsb_env* env, double* dst5, void* stream);
 int32_t bsb_sum_episode_stats_many(bsb_env* const* envs, int32_t count,
                                    double* dst, void* stream);
 
+/*
+ * Per-lane log rows (see bsb_config.log_schedule): row k of lane i holds the
+ * reference wrapper's columns steps, episode, total_return, episode_len,
+ * episode_return followed by the bsuite_info() fields (bsb_info_name order) at
+ * the LAST timestep that completed episode log_schedule[k] of that lane.
+ * bsb_log_layout reports [n_points, n_columns]; bsb_read_log_rows copies
+ * rows float64 [n_points][n_columns][B] and counts int32 [B] (rows recorded so
+ * far per lane) into caller buffers in the environment's memory space.
+ */
+int32_t bsb_log_layout(const bsb_env* env, int32_t* n_points, int32_t* n_columns);
+int32_t bsb_read_log_rows(bsb_env* env, double* rows, int32_t* counts, void* stream);
+
 /* Flat snapshot of all lane state (checkpoint/resume; absent in the reference). */
 int32_t bsb_state_bytes(const bsb_env* env, int64_t* nbytes);
 int32_t bsb_get_state(bsb_env* env, void* dst_host, int64_t nbytes, void* stream);
@@ -270,8 +291,9 @@ int32_t bsb_set_state(bsb_env* env, const void* src_host, int64_t nbytes,
  * `actions` (host, int32 [B]), steps, and delivers the requested outputs into
  * HOST buffers (`host_out`; NULL members are skipped, so an agent that consumes
  * observations on the device passes observation = NULL and supplies
- * `device_obs`, a device pointer that receives them).  Synchronous: on return
- * the outputs have landed and `device_obs` is complete in device memory.  This
+ * `device_obs`, a device pointer that receives them).  Synchronous for the
+ * host outputs: on return they have landed (for `device_obs` see
+ * BSB_HOST_FENCE_CALLER).  This
  * is the call pattern of the reference's agent loop, one env.step(action) per
  * decision (baselines/experiment.py:45-57).
  *
@@ -288,6 +310,15 @@ int32_t bsb_set_state(bsb_env* env, const void* src_host, int64_t nbytes,
  *       bsb_reset / bsb_step / bsb_rollout on `caller_stream` is waited for (on
  *       the device) before the step runs.  Without the flag the caller must
  *       have synchronised that stream: the step runs on a stream the handle owns.
+ *   BSB_HOST_FENCE_CALLER  deep_sea and catch (whose observation is a function
+ *       of the lane state) run host steps in two phases: the transitions of all
+ *       lanes first, then the observation stream.  The call returns as soon as
+ *       the scalars have landed -- the agent decides its next action while the
+ *       observations are still being written.  With this flag `caller_stream`
+ *       is fenced (on the device) behind the step, so work enqueued there
+ *       afterwards sees complete observations; without it, order a consumer by
+ *       the next call on this handle (every entry point waits for the step) or
+ *       set BSB_HOST_EARLY=0 to make the call wait for the whole kernel.
  *   BSB_HOST_PRELAUNCH  (pinned buffers only) after ringing this step, the NEXT
  *       step's kernel is enqueued at once; it becomes resident as this one drains
  *       and polls the mailbox doorbell, so the next call costs neither a launch
@@ -299,6 +330,7 @@ int32_t bsb_set_state(bsb_env* env, const void* src_host, int64_t nbytes,
  */
 #define BSB_HOST_ORDER_AFTER_STREAM 1u
 #define BSB_HOST_PRELAUNCH 2u
+#define BSB_HOST_FENCE_CALLER 4u
 int32_t bsb_step_host(bsb_env* env, const int32_t* actions,
                       const bsb_outputs* host_out, float* device_obs,
                       void* caller_stream, uint32_t flags);

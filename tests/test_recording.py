@@ -145,3 +145,88 @@ def test_load_and_record_modes(tmp_path, capsys):
   assert 'episode = 1 |' in printed and 'total_regret = ' in printed
   with pytest.raises(ValueError, match='Unrecognised logging_mode'):
     bsuite_b200.load_and_record('bandit/0', str(tmp_path), logging_mode='sqlite', device='cpu')
+
+
+# ---------------------------------------------------------------------------- batched, device-side log rows
+_BATCHED_DEVICES = [pytest.param('cpu', id='host'), pytest.param('cuda', id='cuda', marks=pytest.mark.gpu)]
+
+
+def _reference_rows(env_class, kwargs, seed, lane, actions, wrapper=None, arg=None):
+  """Rows the reference's own Logging wrapper writes for one lane (utils/wrappers.py:85-125)."""
+  rr.import_reference()
+  from bsuite.utils import wrappers  # pylint: disable=import-outside-toplevel
+
+  class Rows:
+    def __init__(self):
+      self.rows = []
+
+    def write(self, data):
+      self.rows.append(dict(data))
+
+  raw = rr.make_reference_env(env_class, kwargs, 'philox', seed, lane, wrapper, arg)
+  raw.bsuite_num_episodes = 10000
+  sink = Rows()
+  logged = wrappers.Logging(raw, sink)
+  for a in actions:
+    logged.step(int(a))
+  return sink.rows
+
+
+@pytest.mark.skipif(not rr.reference_available(), reason='/root/reference only exists in the build container')
+@pytest.mark.parametrize('device', _BATCHED_DEVICES)
+def test_batched_log_rows_equal_the_reference_logging_wrapper_row_for_row(device, tmp_path):
+  """64 lanes x 1 000 episodes of catch.  Every lane's rows, recorded on the device at the
+  log-spaced episode counts, equal the rows the reference wrapper writes for the same lane -- and the CSV files
+  written from them load with the reference's csv_load."""
+  import torch
+  B, episodes = 64, 1000
+  T = episodes * 10                                 # catch: 9 transitions + the auto-reset call per episode
+  env = bsuite_b200.load_from_id('catch/0', batch=B, device=device, seed=11, record_rows=True)
+  actions = np.random.RandomState(5).randint(3, size=(T, B)).astype(np.int32)
+  for t0 in range(0, T, 2000):                      # fused rollouts and single steps mixed
+    env.rollout(1999, actions=torch.as_tensor(actions[t0:t0 + 1999]))
+    env.step(torch.as_tensor(actions[t0 + 1999]))
+  logged = env.logged_rows()
+  rows, counts = logged['rows'].cpu().numpy(), logged['counts'].cpu().numpy()
+  assert list(logged['columns']) == ['steps', 'episode', 'total_return', 'episode_len', 'episode_return', 'total_regret']
+  assert (counts == 36).all()                       # 1, 2, ..., 10, 12, ..., 1000: 10 + 13 + 13 rows
+  for lane in range(B):
+    want = _reference_rows('catch', {}, 11, lane, actions[:, lane])
+    assert len(want) == counts[lane]
+    for k, row in enumerate(want):
+      got = dict(zip(logged['columns'], rows[k, :, lane]))
+      assert {c: float(v) for c, v in row.items()} == got, (lane, k)
+  from bsuite.logging import csv_load  # pylint: disable=import-outside-toplevel
+  dirs = recording.write_lane_csvs(env, 'catch/0', str(tmp_path), lanes=range(4))
+  df, _ = csv_load.load_bsuite(dirs[2])
+  assert list(df['episode']) == list(logged['schedule'][:36]) and set(df['bsuite_id']) == {'catch/0'}
+  assert list(df['total_regret']) == [r['total_regret'] for r in _reference_rows('catch', {}, 11, 2, actions[:, 2])]
+  with pytest.raises(ValueError, match='already exists'):
+    recording.write_lane_csvs(env, 'catch/0', str(tmp_path), lanes=range(2))
+
+
+@pytest.mark.skipif(not rr.reference_available(), reason='/root/reference only exists in the build container')
+@pytest.mark.parametrize('device', _BATCHED_DEVICES)
+@pytest.mark.parametrize('bsuite_id,env_class,kwargs,n_act,wrapper,arg', [
+    ('cartpole/0', 'cartpole', {}, 3, None, None),                      # info kept in registers between steps
+    ('deep_sea_stochastic/0', 'deep_sea', dict(size=10, deterministic=False, mapping_seed=42), 2, None, None),
+    ('bandit_scale/3', 'bandit', dict(mapping_seed=3), 11, 'scale', 1.0),
+])
+def test_batched_log_rows_for_other_families(device, bsuite_id, env_class, kwargs, n_act, wrapper, arg):
+  import torch
+  from bsuite_b200 import sweep
+  B, T = 6, 3000
+  env = bsuite_b200.load_from_id(bsuite_id, batch=B, device=device, seed=2, record_rows=True)
+  settings = dict(sweep.SETTINGS[bsuite_id])
+  arg = settings.get('reward_scale', arg)
+  actions = np.random.RandomState(9).randint(n_act, size=(T, B)).astype(np.int32)
+  env.rollout(T, actions=torch.as_tensor(actions))
+  logged = env.logged_rows()
+  rows, counts = logged['rows'].cpu().numpy(), logged['counts'].cpu().numpy()
+  for lane in range(B):
+    want = _reference_rows(env_class, kwargs, 2, lane, actions[:, lane], wrapper, arg)
+    assert len(want) == counts[lane] > 0
+    for k, row in enumerate(want):
+      for c, v in row.items():
+        got = rows[k, list(logged['columns']).index(c), lane]
+        assert got == pytest.approx(float(v), abs=1e-6 if env_class == 'cartpole' and device == 'cuda' else 0), (lane, k, c)
