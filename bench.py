@@ -483,9 +483,11 @@ def engine_main(args):
   host_actions = torch.randint(0, 2, (Ke, B), dtype=torch.int32).pin_memory()
   host_small = env.make_host_buffers(with_observation=False)
 
+  host_rows = [host_actions[i] for i in range(Ke)]
+
   def e2e_loop(n, host, prelaunch):
     for t in range(n):
-      env.step_host(host_actions[t % Ke], host, out=ring[t % RING], prelaunch=prelaunch)
+      env.step_host(host_rows[t % Ke], host, out=ring[t % RING], prelaunch=prelaunch)
     env.host_flush()
 
   def timed_e2e(n, host, reps, prelaunch=False):
@@ -513,7 +515,7 @@ def engine_main(args):
   # result, as in this random-action workload): env.step() given a pinned host action tensor and outputs whose
   # scalars live in pinned host memory -- the kernel reads / writes them in place; one synchronise at the end.
   mixed = [env.make_mixed_buffers() for _ in range(RING)]
-  action_rows = [host_actions[i] for i in range(Ke)]
+  action_rows = host_rows
   for t in range(5):
     env.step(action_rows[t % Ke], out=mixed[t % RING])
   torch.cuda.synchronize()

@@ -28,7 +28,8 @@ class Config(ctypes.Structure):           # struct bsb_config, field for field (
           'unscaled_move_cost', 'height_threshold', 'x_threshold', 'timescale', 'max_time', 'init_range',
           'theta_dot_threshold', 'x_reward_threshold', 'move_cost', 'noise_scale', 'reward_scale')] + [
               ('table', ctypes.c_void_p), ('table_bytes', ctypes.c_int64),
-              ('table2', ctypes.c_void_p), ('table2_bytes', ctypes.c_int64)])
+              ('table2', ctypes.c_void_p), ('table2_bytes', ctypes.c_int64),
+              ('log_schedule', ctypes.c_void_p), ('log_schedule_len', ctypes.c_int64)])
 
 
 class Outputs(ctypes.Structure):          # struct bsb_outputs

@@ -98,6 +98,9 @@ def main():
       graphed.actions.copy_(acts[:G])
       graph_s = measure(lambda i=0: graphed.replay(), max(3, args.steps // G), warm=2) / G
       del graphed
+      # the same handle stepped EAGERLY afterwards: it stays in graph-safe mode (step counter and chunk scheduler
+      # on the device), so this isolates the mode's kernel-side cost from the graph launch mechanics
+      gsafe_s = measure(lambda i=0: genv.step(acts[i % acts.shape[0]], out=ring[i % ring_n]), args.steps)
       genv.close()
     row = dict(name=name, batch=batch, obs_numel=numel, bytes_per_lane_step=bytes_per,
                step_us=step_s * 1e6, step_steps_per_s=batch / step_s, step_gbs=batch * bytes_per / step_s / 1e9,
@@ -107,9 +110,9 @@ def main():
     print(f"{name:32s} B={batch:8d} K={numel:5d}  step {row['step_us']:8.1f} us {row['step_steps_per_s']:.3e}/s "
           f"{row['step_gbs']:7.0f} GB/s | rollout(T={T}) {row['rollout_us_per_step']:8.1f} us/step "
           f"{row['rollout_steps_per_s']:.3e}/s {row['rollout_gbs']:7.0f} GB/s"
-          + ('' if graph_s is None else f" | graph {graph_s * 1e6:7.1f} us/step"), flush=True)
+          + ('' if graph_s is None else f" | graph {graph_s * 1e6:7.1f} us/step, eager in graph-safe mode {gsafe_s * 1e6:7.1f}"), flush=True)
     if graph_s is not None:
-      row.update(graph_us_per_step=graph_s * 1e6, graph_steps_per_s=batch / graph_s)
+      row.update(graph_us_per_step=graph_s * 1e6, graph_steps_per_s=batch / graph_s, graph_safe_eager_us=gsafe_s * 1e6)
     env.close()
     del ring, rbuf, acts
     torch.cuda.empty_cache()

@@ -65,7 +65,7 @@ for bsuite_id, batch in (('deep_sea/11', 20000), ('catch/0', 3000), ('mnist/0', 
 # One-launch reduction over several environments and a whole lock-step in one graph.
 from bsuite_b200 import suite
 ids = ['catch/0', 'deep_sea/0', 'bandit_noise/0', 'cartpole/0', 'mnist/0', 'umbrella_length/0']
-a, b = suite.SweepBatch(ids, lanes=300, device='cuda', seed=1), suite.SweepBatch(ids, lanes=300, device='cuda', seed=1)
+a, b = suite.SweepBatch(ids, lanes=300, device='cuda', seed=1), suite.SweepBatch(ids, lanes=300, device='cuda', seed=1, ring=2)
 graphed = a.capture(1, lock_steps=2)
 for _ in range(3):
   got, want = graphed.replay(), [b.rollout(1), b.rollout(1)]
