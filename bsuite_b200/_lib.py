@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get('BSB_LIBRARY') or os.path.join(_HERE, 'libbsuite_b200.
 ABI_VERSION = 5
 DEVICE_HOST = -1
 MAX_INFO = 4
+COMM_ID_BYTES = 128
 
 # enum bsb_family
 DEEP_SEA, CATCH, CARTPOLE, CARTPOLE_SWINGUP, MOUNTAIN_CAR, MEMORY_CHAIN, BANDIT, UMBRELLA_CHAIN, \
@@ -93,6 +94,14 @@ EXPORTS = {
                                        ctypes.c_void_p, ctypes.c_uint32]),
     'bsb_host_flush': (ctypes.c_int32, [ctypes.c_void_p]),
     'bsb_invalid_actions': (ctypes.c_int32, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32)]),
+    'bsb_comm_unique_id': (ctypes.c_int32, [ctypes.c_void_p]),
+    'bsb_comm_create': (ctypes.c_int32, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                         ctypes.POINTER(ctypes.c_void_p)]),
+    'bsb_comm_destroy': (ctypes.c_int32, [ctypes.c_void_p]),
+    'bsb_comm_world': (ctypes.c_int32, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]),
+    'bsb_log_point': (ctypes.c_int32, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int32, ctypes.c_void_p,
+                                       ctypes.c_void_p, ctypes.c_void_p]),
+    'bsb_comm_wait': (ctypes.c_int32, [ctypes.c_void_p, ctypes.c_void_p]),
     'bsb_launch_count': (ctypes.c_int64, []),
 }
 

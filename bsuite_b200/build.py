@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 FAMILIES = ('deep_sea', 'catch', 'cartpole', 'cartpole_swingup', 'mountain_car', 'memory_chain', 'bandit',
             'umbrella_chain', 'discounting_chain', 'mnist')
-SOURCES = [os.path.join(CSRC, 'bsb_engine.cu')] + [os.path.join(CSRC, f'fam_{name}.cu') for name in FAMILIES]
+SOURCES = [os.path.join(CSRC, 'bsb_engine.cu'), os.path.join(CSRC, 'bsb_comm.cu')] + [os.path.join(CSRC, f'fam_{name}.cu') for name in FAMILIES]
 HEADERS = [os.path.join(CSRC, f) for f in ('bsb_rng.cuh', 'bsb_families.cuh', 'bsb_kernels.cuh', 'bsb_env.h',
                                            'bsb_dispatch.cuh')] + [
     os.path.join(os.path.dirname(HERE), 'include', 'bsuite_b200.h')]
@@ -79,7 +79,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     for log in pool.map(lambda src: _compile(nvcc, src, verbose), todo):
       if verbose:
         sys.stderr.write(log)
-  cmd = [nvcc, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', OUTPUT] + [_object_path(s) for s in SOURCES]
+  cmd = [nvcc, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', OUTPUT] + [_object_path(s) for s in SOURCES] + ['-ldl']
   proc = subprocess.run(cmd, capture_output=True, text=True)
   if proc.returncode != 0:
     raise RuntimeError('link failed:\n' + ' '.join(cmd) + '\n' + proc.stdout + proc.stderr)

@@ -149,6 +149,65 @@ class LogPoint:
         current.wait_event(self._done[t % self._slots])
 
 
+class NativeLogPoint:
+  """`LogPoint` without torch.distributed on the data path: the C ABI's own communicator (`bsb_comm_*`, NCCL
+  loaded by the library at run time) -- what a non-Python FFI host uses.  The 128-byte NCCL id still has to reach
+  every rank once; here it travels through `torch.distributed` if that is initialised (any backend), else pass
+  `unique_id` / `rank` / `world` yourself.  One ticket in flight: `issue()` then `result()`.
+  """
+
+  def __init__(self, envs, unique_id: Optional[bytes] = None, rank: Optional[int] = None, world: Optional[int] = None):
+    import torch
+    import torch.distributed as dist
+    self._torch = torch
+    self.envs = list(envs) if isinstance(envs, (list, tuple)) else [envs]
+    self._device = self.envs[0].device
+    if self._device.type != 'cuda':
+      raise RuntimeError('NativeLogPoint needs CUDA environments')
+    self._lib = _lib.load()
+    if rank is None or world is None:
+      rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_initialized() else (0, 1)
+    if unique_id is None:
+      box = [None]
+      if rank == 0:
+        buf = (ctypes.c_uint8 * _lib.COMM_ID_BYTES)()
+        _lib.check(self._lib.bsb_comm_unique_id(buf))
+        box[0] = bytes(buf)
+      if world > 1:
+        dist.broadcast_object_list(box, src=0)
+      unique_id = box[0]
+    self.rank, self.world = rank, world
+    handle = ctypes.c_void_p()
+    buf = (ctypes.c_uint8 * _lib.COMM_ID_BYTES).from_buffer_copy(unique_id)
+    _lib.check(self._lib.bsb_comm_create(buf, rank, world, self._device.index, ctypes.byref(handle)))
+    self._comm = handle
+    n = len(self.envs)
+    self._local = torch.zeros((n, 5), dtype=torch.float64, device=self._device)
+    self._gathered = torch.zeros((world, n, 5), dtype=torch.float64, device=self._device)
+    self._handles = (ctypes.c_void_p * n)(*[env._handle.ptr.value for env in self.envs])  # pylint: disable=protected-access
+
+  def issue(self):
+    stream = self.envs[0]._stream()  # pylint: disable=protected-access
+    _lib.check(self._lib.bsb_log_point(self._comm, self._handles, len(self.envs), self._local.data_ptr(),
+                                       self._gathered.data_ptr(), stream))
+
+  def result(self):
+    """`[world, n_envs, 5]`; the caller's current stream is fenced behind the gather (the host does not block)."""
+    _lib.check(self._lib.bsb_comm_wait(self._comm, self.envs[0]._stream()))  # pylint: disable=protected-access
+    return self._gathered
+
+  def close(self):
+    if self._comm is not None:
+      self._lib.bsb_comm_destroy(self._comm)
+      self._comm = None
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:  # interpreter shutdown
+      pass
+
+
 def gather_lane_tensor(tensor, group=None):
   """All-gather of a per-lane tensor [B_rank, ...] into [sum B_rank, ...] (equal shards only)."""
   import torch

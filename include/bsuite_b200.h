@@ -348,6 +348,35 @@ int32_t bsb_host_flush(bsb_env* env);
  */
 int32_t bsb_invalid_actions(bsb_env* env, int32_t* seen);
 
+/*
+ * Multi-GPU log points without torch.distributed ("one collective:
+ * ncclAllGather of a per-rank stats block at log points only").  One process per
+ * GPU; rank 0 calls bsb_comm_unique_id and shares the 128 bytes out of band (a
+ * file, a socket, MPI, torch's store), every rank calls bsb_comm_create.  NCCL is
+ * loaded at run time (BSB_NCCL_LIBRARY, else libnccl.so.2): single-GPU callers
+ * never need it.
+ *
+ * bsb_log_point: the Logging sums of `count` environments of this rank are
+ * reduced by ONE kernel on `stream` into local [count][5] and all-gathered into
+ * gathered [world][count][5] on a side stream the communicator owns, fenced by
+ * events -- `stream` is free to run the next steps at once (the reference writes
+ * log rows at log-spaced episodes only: utils/wrappers.py:99-110).  local and
+ * gathered are caller-owned device buffers that must stay valid until
+ * bsb_comm_wait(comm, s), which makes stream `s` wait (on the device) for the
+ * latest gather.  Replaces the process pool's result collection of
+ * bsuite/baselines/utils/pool.py:28-54.
+ */
+#define BSB_COMM_ID_BYTES 128
+typedef struct bsb_comm bsb_comm;
+int32_t bsb_comm_unique_id(uint8_t* id /* [BSB_COMM_ID_BYTES] */);
+int32_t bsb_comm_create(const uint8_t* id, int32_t rank, int32_t world,
+                        int32_t device, bsb_comm** out);
+int32_t bsb_comm_destroy(bsb_comm* comm);
+int32_t bsb_comm_world(const bsb_comm* comm, int32_t* rank, int32_t* world);
+int32_t bsb_log_point(bsb_comm* comm, bsb_env* const* envs, int32_t count,
+                      double* local, double* gathered, void* stream);
+int32_t bsb_comm_wait(bsb_comm* comm, void* stream);
+
 /* Number of kernels this library has launched in this process (bench evidence). */
 int64_t bsb_launch_count(void);
 

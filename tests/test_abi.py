@@ -136,3 +136,19 @@ def test_abi_fuzzer_finds_no_crash():
                         capture_output=True, text=True, timeout=300)
   assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-2000:]
   assert 'no crash' in proc.stdout
+
+
+def test_communicator_entry_points_validate_their_arguments():
+  """bsb_comm_* (NCCL resolved at run time): the id can be drawn without a GPU; creation needs a CUDA device."""
+  import ctypes
+  lib = _lib.load()
+  buf = (ctypes.c_uint8 * _lib.COMM_ID_BYTES)()
+  status = lib.bsb_comm_unique_id(buf)
+  if status != 0:                         # no NCCL library on this machine: reported, not crashed
+    assert b'NCCL' in lib.bsb_last_error()
+    return
+  assert any(bytes(buf))
+  handle = ctypes.c_void_p()
+  assert lib.bsb_comm_create(buf, 3, 2, 0, ctypes.byref(handle)) != 0 and not handle.value      # rank >= world
+  assert lib.bsb_comm_create(None, 0, 1, 0, ctypes.byref(handle)) != 0
+  assert lib.bsb_comm_destroy(None) == 0 and lib.bsb_comm_wait(None, None) != 0
