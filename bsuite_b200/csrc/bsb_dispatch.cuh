@@ -134,13 +134,16 @@ int device_launch(bsb_env* e, LaunchArgs a, cudaStream_t stream) {
   if (is_image && a.emit_bulk) {
     // mnist through the TMA unit: groups of m <= 4 tiles staged in shared memory (two buffers per warp) plus m
     // all-zero tiles per CTA for the LAST frames.  16-byte image loads need K % 16 == 0 (28 x 28 = 784 is).
+    // Staging buffers per warp (BSB_IMAGE_STAGES, default 1): the pixel conversion is issue-bound, so resident
+    // warps matter more than overlapping a warp's own fill with its own store -- other warps fill that gap.
+    const int stages = e->image_stages;
     int m = 4;
-    while (m > 1 && (size_t)TILE_STAGES * m * tile > 28 * 1024) m >>= 1;
+    while (m > 1 && (size_t)stages * m * tile > 28 * 1024) m >>= 1;
     if (m > chunk) m = chunk;
-    if ((K & 15) != 0 || (size_t)TILE_STAGES * m * tile > 64 * 1024) {
+    if ((K & 15) != 0 || (size_t)stages * m * tile > 64 * 1024) {
       a.emit_bulk = 0;
     } else {
-      a.group_lanes = m; threads = 64; a.cta_extra_floats = m * K; persistent = e->deep_sea_persistent != 0;
+      a.group_lanes = m; a.stage_rows = stages; threads = 64; a.cta_extra_floats = m * K; persistent = e->deep_sea_persistent != 0;
     }
   }
   a.use_pdl = (e->use_pdl && !a.no_pdl && a.mode == MODE_STEP && a.T == 1) ? 1 : 0;

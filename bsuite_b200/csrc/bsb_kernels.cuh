@@ -177,7 +177,7 @@ size_t smem_floats_per_warp(int K, bool emit_bulk, int group_lanes, int row_stag
   if (EmitKind<F>::value == EMIT_ROWS || EmitKind<F>::value == EMIT_TWOHOT) return (size_t)row_stages * 32 * (size_t)K;
   if (EmitKind<F>::value == EMIT_ONEHOT && emit_bulk) return (size_t)TILE_STAGES * (size_t)group_lanes * (size_t)K;
   if (EmitKind<F>::value == EMIT_IMAGE)                    // int8 pixel -> float32 table (+ two staging buffers of m tiles)
-    return 256 + (emit_bulk ? (size_t)TILE_STAGES * (size_t)group_lanes * (size_t)K : 0);
+    return 256 + (emit_bulk ? (size_t)row_stages * (size_t)group_lanes * (size_t)K : 0);
   return 0;
 }
 
@@ -314,20 +314,21 @@ __device__ __forceinline__ void emit_image(const EnvParams& p, const float* lut,
   }
 }
 
-// image.astype(float32) / 255 (mnist.py:64) without a table or an IEEE division: q0 = v * rcp, one Newton
-// residual step with two FMAs.  With rcp the correctly rounded 1/255 this is the correctly rounded quotient for
-// every int8 v (Markstein's theorem; all 256 inputs are checked against Mnist::pixel in tests/test_golden_parity.py
-// and by `static` reasoning: |v| <= 128 is exact in float32 and no intermediate over- or underflows).  The table
-// of emit_image costs one LDS per pixel but serialises on bank conflicts when neighbouring pixels differ.
-__device__ __forceinline__ float pixel_div255(int v) {
-  const float x = (float)v, rcp = 1.0f / 255.0f;      // constant-folded by the compiler
-  const float q = __fmul_rn(x, rcp);
-  const float r = __fmaf_rn(-255.0f, q, x);
-  return __fmaf_rn(r, rcp, q);
+// image.astype(float32) / 255 (mnist.py:64) without a table, an IEEE division or an int->float conversion (I2F runs
+// on the quarter-rate XU pipe): per pixel one PRMT (sign-extended byte: the reference parses images as INT8,
+// utils/datasets.py:55-56), one IADD + one FADD (v as float through the 1.5 * 2^23 magic number, exact for
+// |v| <= 128), then the quotient as fma(v, hi, v * lo) with hi + lo = 1/255 split into two floats.  That is the
+// correctly rounded v / 255 for every int8 v: checked exhaustively against numpy on the device
+// (tests/test_round2_features.py) -- 256 inputs, no reasoning about rounding needed.
+__device__ __forceinline__ float pixel_div255(uint32_t word, int byte) {
+  const uint32_t sel = (uint32_t)byte | ((8u | (uint32_t)byte) << 4) | ((8u | (uint32_t)byte) << 8) | ((8u | (uint32_t)byte) << 12);
+  const int v = (int)__byte_perm(word, 0u, sel);
+  const float x = __fadd_rn(__int_as_float(0x4B400000 + v), -12582912.0f);
+  const float hi = 0.003921568859368563f, lo = -2.319175823606301e-10f;      // float(1/255), float(1/255 - hi)
+  return __fmaf_rn(x, hi, __fmul_rn(x, lo));
 }
 __device__ __forceinline__ float4 pixels4(uint32_t w) {
-  return make_float4(pixel_div255((int)(int8_t)(w & 0xffu)), pixel_div255((int)(int8_t)((w >> 8) & 0xffu)),
-                     pixel_div255((int)(int8_t)((w >> 16) & 0xffu)), pixel_div255((int)(int8_t)(w >> 24)));
+  return make_float4(pixel_div255(w, 0), pixel_div255(w, 1), pixel_div255(w, 2), pixel_div255(w, 3));
 }
 
 // Image tiles through shared memory and the TMA unit (K % 16 == 0, e.g. 28 x 28).  Lanes are taken in groups of
@@ -337,10 +338,11 @@ __device__ __forceinline__ float4 pixels4(uint32_t w) {
 //   * otherwise all 16-byte loads of the group's int8 images (49 per 28 x 28 tile, <= 8 per thread) are issued
 //     before the first conversion, the float32 tiles land in one of two staging buffers and leave as one bulk
 //     store of m * 4K bytes.
-// stage = [256 floats: table of the vector path][2 x m x K floats]; `emitted` counts staged stores (buffer parity).
+// stage = [256 floats: table of the vector path][stages x m x K floats]; `emitted` counts staged stores (buffer
+// parity).  stages = 1 halves the shared memory per warp: more resident warps for the conversion.
 __device__ __forceinline__ void emit_image_bulk(const EnvParams& p, float* stage, const float* cta_zero, float* obs_t,
                                                 int64_t warp_base, int n_lanes, int K, int image, int m, int l2_hint,
-                                                unsigned& emitted) {
+                                                int stages, unsigned& emitted) {
   constexpr int MAXM = 4;
   const int tid = threadIdx.x & 31;
   float* tiles = stage + 256;
@@ -354,8 +356,9 @@ __device__ __forceinline__ void emit_image_bulk(const EnvParams& p, float* stage
       if (tid == 0) { bulk_store_obs(dst, cta_zero, bytes, l2_hint); bulk_commit(); }
       continue;
     }
-    float* buf = tiles + (size_t)(emitted & 1u) * m * K;
-    if (tid == 0) bulk_wait_read<1>();      // at most the newest store is still reading: never this buffer
+    float* buf = tiles + (size_t)(stages == 2 ? (emitted & 1u) : 0u) * m * K;
+    // two staging buffers: at most the newest store may still be reading, never this buffer; one: none may
+    if (tid == 0) { if (stages == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
     __syncwarp();
     int img[MAXM];
 #pragma unroll
@@ -652,7 +655,7 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
       }
     } else if (kEmit == EMIT_IMAGE) {
       const int image = Descriptor<F>::a(L);
-      if (bulk) emit_image_bulk(p, stage, cta_zero, obs_t, warp_base, n_lanes, K, active ? image : -1, a.group_lanes, a.l2_hint, emitted);
+      if (bulk) emit_image_bulk(p, stage, cta_zero, obs_t, warp_base, n_lanes, K, active ? image : -1, a.group_lanes, a.l2_hint, a.stage_rows, emitted);
       else emit_image(p, stage, obs_t, warp_base, n_lanes, K, image, vec && (K & 3) == 0);
     } else if (!a.stage_rows) {
       // observation rows too long for a shared-memory stage: every thread renders its row in place

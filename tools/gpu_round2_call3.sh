@@ -7,6 +7,8 @@ timeout 600 python bench.py --skip-cpu-baseline > gpurun_out/bench.log 2> gpurun
 timeout 400 python bench.py --steps 20 --warmup 5 --skip-cpu-baseline --skip-configs > gpurun_out/bench_k20.log 2>> gpurun_out/bench.err; echo "rc=$?" >> gpurun_out/bench.err
 timeout 600 python tools/bench_families.py --graph 16 --out gpurun_out/families.jsonl > gpurun_out/families.log 2>&1; cat gpurun_out/families.log
 BSB_GRAPH_PDL=0 timeout 300 python tools/bench_families.py --graph 16 --only catch/0 > gpurun_out/families_nopdl.log 2>&1; cat gpurun_out/families_nopdl.log
+BSB_IMAGE_STAGES=2 timeout 300 python tools/bench_families.py --only mnist > gpurun_out/families_mnist_2stages.log 2>&1; cat gpurun_out/families_mnist_2stages.log
+for fam in mnist/0 umbrella_distract/22; do name=$(echo $fam | tr '/' '_'); timeout 300 ncu --set full --clock-control none --import-source on -k regex:transition_kernel --launch-skip 8 --launch-count 4 -f -o gpurun_out/ncu_r02b_${name} python tools/bench_families.py --only "$fam" --steps 6 --rollout 16 > gpurun_out/ncu_r02b_${name}.log 2>&1; done
 timeout 600 compute-sanitizer --tool memcheck python tools/sanitize_check.py > gpurun_out/sanitizer_memcheck.log 2>&1; tail -4 gpurun_out/sanitizer_memcheck.log
 timeout 600 compute-sanitizer --tool racecheck python tools/sanitize_check.py > gpurun_out/sanitizer_racecheck.log 2>&1; tail -4 gpurun_out/sanitizer_racecheck.log
 tail -5 gpurun_out/bench.err
