@@ -752,6 +752,7 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
           // a dynamically dealt chunk: some other warp ran its phase 1 -- long ago in practice, but wait for it
           if (tid == 0) while (a.mail->phase1 != a.ticket) {}
           __syncwarp();
+          __threadfence();                   // acquire: the loads below must not be served from a stale L1 line
           F::init(p, L);
           if (active) { F::load(p, lane, L); F::describe(p, L); }
         }

@@ -424,7 +424,7 @@ class BatchedEnvironment:
     torch.cuda.synchronize(self._device)
     self.load_state_dict(state)
     graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph):
+    with torch.cuda.graph(graph, capture_error_mode='thread_local'):   # other threads (NCCL watchdog) may touch CUDA
       record()
     return GraphedSteps(self, graph, actions, buffers)
 

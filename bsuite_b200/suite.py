@@ -121,7 +121,7 @@ class SweepBatch:
       env.load_state_dict(states[k])
     self._turn = 0
     graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph):
+    with torch.cuda.graph(graph, capture_error_mode='thread_local'):   # other threads (NCCL watchdog) may touch CUDA
       results = [self.rollout(num_steps, action_seed=action_seed) for _ in range(lock_steps)]
     return GraphedSweep(graph, results[0] if lock_steps == 1 else results)
 

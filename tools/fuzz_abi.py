@@ -50,6 +50,11 @@ def main():
         cfg.table, cfg.table_bytes = table.ctypes.data, rng.choice([0, 1, 4, 25, 36, 40, 88, 100, 784, 1 << 16, -1])
       if rng.random() < 0.5:
         cfg.table2, cfg.table2_bytes = table.ctypes.data, rng.choice([0, 1, 10, 1 << 16, -1])
+    schedule = np.array(sorted(rng.sample(range(1, 200), 5)), np.int64)
+    if rng.random() < 0.3:                   # a log schedule: valid (needs flag 1), or hostile (unsorted / wrong length)
+      if not plausible and rng.random() < 0.5:
+        schedule = schedule[::-1].copy()
+      cfg.log_schedule, cfg.log_schedule_len = schedule.ctypes.data, (5 if plausible else rng.choice([-1, 0, 5, 1 << 20]))
     batch = rng.choice([1, 3, 33, 70]) if plausible else rng.choice([-1, 0, 1, 3, 33])
     handle = ctypes.c_void_p()
     status = lib.bsb_create(ctypes.byref(cfg), batch, _lib.DEVICE_HOST, rng.choice([0, 5, 2**32, 2**63]),
@@ -73,8 +78,16 @@ def main():
       if rng.random() < 0.7: out.reward_f64 = reward64.ctypes.data
       if rng.random() < 0.7: out.discount = discount.ctypes.data
       if rng.random() < 0.7: out.step_type = step_type.ctypes.data
-      # like the reference, actions are not validated against action_spec(): only in-range ones are defined
       acts = np.array([rng.randrange(n_act.value) for _ in range(T * batch)], np.int32)
+      hostile = acts.copy()                       # out-of-range actions must be REJECTED on the host path, state untouched
+      hostile[rng.randrange(batch)] = rng.choice([-1, n_act.value, 255, 1 << 20, -(1 << 31), (1 << 31) - 1])
+      assert lib.bsb_step(handle, ctypes.c_void_p(hostile.ctypes.data), ctypes.byref(out), None) != 0
+      assert lib.bsb_rollout(handle, T, ctypes.c_void_p(hostile.ctypes.data), 0, ctypes.byref(out), None, None) != 0
+      assert lib.bsb_step_host(handle, ctypes.c_void_p(hostile.ctypes.data), ctypes.byref(out), None, None, rng.choice([0, 1, 2, 4, 7])) != 0
+      seen = ctypes.c_int32(7)
+      assert lib.bsb_invalid_actions(handle, ctypes.byref(seen)) == 0 and seen.value == 0
+      assert lib.bsb_step_host(handle, ctypes.c_void_p(acts.ctypes.data), ctypes.byref(out), None, None, rng.choice([0, 1, 2, 4, 7])) == 0
+      assert lib.bsb_host_flush(handle) == 0
       for _ in range(4):
         lib.bsb_step(handle, ctypes.c_void_p(acts.ctypes.data), ctypes.byref(out), None)
         lib.bsb_rollout(handle, T, ctypes.c_void_p(acts.ctypes.data) if rng.random() < 0.5 else None, rng.getrandbits(64),
@@ -88,6 +101,14 @@ def main():
       lib.bsb_read_info(handle, index, ctypes.c_void_p(column.ctypes.data), None)
       lib.bsb_read_episode_stats(handle, index, ctypes.c_void_p(column.ctypes.data), None)
     lib.bsb_sum_episode_stats(handle, ctypes.c_void_p(column.ctypes.data), None)
+    many = (ctypes.c_void_p * 2)(handle.value, handle.value)
+    wide = np.zeros(16, np.float64)
+    lib.bsb_sum_episode_stats_many(many, 2, ctypes.c_void_p(wide.ctypes.data), None)
+    assert lib.bsb_sum_episode_stats_many(many, 0, ctypes.c_void_p(wide.ctypes.data), None) != 0
+    points, cols = ctypes.c_int32(), ctypes.c_int32()
+    assert lib.bsb_log_layout(handle, ctypes.byref(points), ctypes.byref(cols)) == 0
+    if points.value == 0:
+      assert lib.bsb_read_log_rows(handle, ctypes.c_void_p(wide.ctypes.data), ctypes.c_void_p(wide.ctypes.data), None) != 0
     nbytes = ctypes.c_int64()
     lib.bsb_state_bytes(handle, ctypes.byref(nbytes))
     if nbytes.value < 50_000_000:

@@ -9,9 +9,9 @@ OUT=/tmp/bsb_asan
 LOG=${1:-/tmp/bsb_asan/run.log}
 mkdir -p $OUT
 cd "$(dirname "$0")/../bsuite_b200/csrc"
-ls bsb_engine.cu fam_*.cu | xargs -P 16 -I{} sh -c "nvcc -gencode arch=compute_100a,code=sm_100a -O1 -std=c++17 --fmad=false \
+ls bsb_engine.cu bsb_comm.cu fam_*.cu | xargs -P 16 -I{} sh -c "nvcc -gencode arch=compute_100a,code=sm_100a -O1 -std=c++17 --fmad=false \
   -Xcompiler -fPIC,-ffp-contract=off,-O1,-g,-fsanitize=address,-fsanitize=undefined,-fno-omit-frame-pointer -c {} -o $OUT/\$(basename {} .cu).o"
-nvcc -shared -o $OUT/libbsuite_b200.so $OUT/*.o -cudart static -Xcompiler -fsanitize=address,-fsanitize=undefined 2>/dev/null
+nvcc -shared -o $OUT/libbsuite_b200.so $OUT/*.o -cudart static -ldl -Xcompiler -fsanitize=address,-fsanitize=undefined 2>/dev/null
 cd ../..
 set +e
 LD_PRELOAD="$(gcc -print-file-name=libasan.so) $(gcc -print-file-name=libubsan.so)" ASAN_OPTIONS=detect_leaks=0 \
