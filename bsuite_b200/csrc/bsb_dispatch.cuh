@@ -167,7 +167,7 @@ int device_launch(bsb_env* e, LaunchArgs a, cudaStream_t stream) {
     const int64_t resident = (int64_t)e->num_sms * (per_sm < 1 ? 1 : (per_sm > 16 ? 16 : per_sm));
     if (grid > resident) {
       grid = resident;
-      a.work_counter = a.clock ? a.clock + 1 : e->work_counter;
+      a.work_counter = a.clock ? a.clock + CLOCK_CHUNK : e->work_counter;
       a.work_base = a.clock ? 0ull : e->work_base;
     } else {
       persistent = false;      // everything is resident anyway: one chunk per warp

@@ -802,7 +802,10 @@ int32_t bsb_set_state(bsb_env* env, const void* src_host, int64_t nbytes, void* 
     // into the device clock as an offset from that base (two's complement, so it may be "negative").
     const unsigned long long since = (unsigned long long)restored - (unsigned long long)env->steps_done;
     BSB_CUDA(cudaDeviceSynchronize());
-    BSB_CUDA(cudaMemcpy(env->clock, &since, sizeof(since), cudaMemcpyHostToDevice));
+    unsigned long long replicas[CLOCK_GROUPS];
+    for (int r = 0; r < CLOCK_GROUPS; ++r) replicas[r] = since;
+    BSB_CUDA(cudaMemcpy2D(env->clock, 16 * sizeof(unsigned long long), replicas, sizeof(unsigned long long),
+                          sizeof(unsigned long long), CLOCK_GROUPS, cudaMemcpyHostToDevice));
   } else {
     env->steps_done = restored;
   }

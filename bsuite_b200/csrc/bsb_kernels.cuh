@@ -453,10 +453,11 @@ template <> struct Descriptor<Mnist> {
 //     failing fetch per warp), so launch k starts at work_base_k = work_base_(k-1) + C.
 // Graph-safe mode (a.clock != null; the handle switches to it for good the first time one of its launches is
 // captured into a CUDA graph): launch arguments are frozen in a graph, so everything that changes from launch to
-// launch lives in device memory instead.  clock[0] = steps this handle has advanced since the switch (step index
-// = a.step0 + clock[0]: the on-device action stream and the Logging columns depend on it), clock[1] = chunk
-// counter, clock[2] = CTAs that have finished.  The CTA that finishes last advances clock[0] by T and zeroes the
-// other two; every CTA reads clock[0] before it counts itself finished, so the update cannot overtake a reader.
+// launch lives in device memory instead (layout: CLOCK_* below): the steps this handle has advanced since the
+// switch (step index = a.step0 + that count: the on-device action stream and the Logging columns depend on it), the
+// chunk counter, and the count of finished CTAs.  The CTA that finishes last advances the step count by T and
+// zeroes the other two; every CTA reads the step count before it counts itself finished, so the update cannot
+// overtake a reader.
 // Register budget per family (second __launch_bounds__ argument, counted in 128-thread blocks per SM).  The
 // generic kernel is register-hungry (two Philox streams, action stream, accumulators); left alone ptxas takes
 // 160-220 registers and 64-thread CTAs then run at 8 warps/SM, which starves the latency-bound small families.
@@ -483,11 +484,17 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-// Graph-safe mode keeps {steps, chunk counter, finished groups} in clock[0..2]; the finished-CTA count is split
-// over CLOCK_GROUPS counters, each on its own 128-byte line (clock[CLOCK_SUB0 + 16 g]), so that a large grid's
-// exit atomics land on 32 addresses instead of one (same-address atomics serialise at ~2 ns each: 2 048 CTAs cost
-// catch 3 us per step; 64 per address cost 0.1 us).
-static const int CLOCK_GROUPS = 32, CLOCK_SUB0 = 16, CLOCK_WORDS = CLOCK_SUB0 + 16 * CLOCK_GROUPS;
+// Graph-safe mode keeps the step count, the chunk counter and the finished-CTA count in device memory.  Every
+// word that many CTAs touch is spread over CLOCK_GROUPS 128-byte lines, because same-line traffic serialises in
+// one L2 slice (~2 ns per access): a 16 384-CTA launch reads the step count once per warp and counts itself out
+// once per CTA.
+//   clock[16 r]                 r < 32: the step count, REPLICATED (CTA b reads replica b % 32; the last CTA of
+//                               a launch rewrites all 32); the host reads / writes replica 0 .. 31
+//   clock[CLOCK_CHUNK]          chunk counter of the persistent grids (a line of its own)
+//   clock[CLOCK_TOP]            groups that have finished
+//   clock[CLOCK_SUB0 + 16 g]    CTAs of group g (= blockIdx % 32) that have finished
+static const int CLOCK_GROUPS = 32, CLOCK_CHUNK = 16 * CLOCK_GROUPS, CLOCK_TOP = CLOCK_CHUNK + 16,
+                 CLOCK_SUB0 = CLOCK_TOP + 16, CLOCK_WORDS = CLOCK_SUB0 + 16 * CLOCK_GROUPS;
 
 template <class F, int RK, bool kNoise, bool kTrack>
 __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kernel(const EnvParams p, const LaunchArgs a) {
@@ -523,7 +530,7 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
   // to become resident: its CTAs park at their own wait, so at most one dependent grid is ever pending.
   if (a.use_pdl) { pdl_wait(); pdl_launch_dependents(); }
   int64_t step0 = a.step0;
-  if (a.clock) step0 += (int64_t)*reinterpret_cast<volatile unsigned long long*>(a.clock);
+  if (a.clock) step0 += (int64_t)*reinterpret_cast<volatile unsigned long long*>(a.clock + 16 * (blockIdx.x % CLOCK_GROUPS));
 
   // Caller-owned buffers: launch arguments, or -- doorbell mode -- whatever the host wrote into the mailbox
   // before it rang this launch's ticket.
@@ -872,10 +879,11 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
       __threadfence();
       if (atomicAdd(sub, 1ull) == (unsigned long long)members - 1ull) {
         *sub = 0ull;                          // re-armed for the next launch (which starts after this one ends)
-        if (atomicAdd(a.clock + 2, 1ull) == (unsigned long long)groups - 1ull) {
-          a.clock[0] = (unsigned long long)(step0 - a.step0) + (a.mode == MODE_INIT ? 0ull : (unsigned long long)a.T);
-          a.clock[1] = 0ull;
-          a.clock[2] = 0ull;
+        if (atomicAdd(a.clock + CLOCK_TOP, 1ull) == (unsigned long long)groups - 1ull) {
+          const unsigned long long steps = (unsigned long long)(step0 - a.step0) + (a.mode == MODE_INIT ? 0ull : (unsigned long long)a.T);
+          for (int r = 0; r < CLOCK_GROUPS; ++r) a.clock[16 * r] = steps;
+          a.clock[CLOCK_CHUNK] = 0ull;
+          a.clock[CLOCK_TOP] = 0ull;
         }
       }
     }
