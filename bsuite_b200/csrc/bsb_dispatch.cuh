@@ -132,18 +132,24 @@ int device_launch(bsb_env* e, LaunchArgs a, cudaStream_t stream) {
     }
   }
   if (is_image && a.emit_bulk) {
-    // mnist through the TMA unit: groups of m <= 4 tiles staged in shared memory (two buffers per warp) plus m
-    // all-zero tiles per CTA for the LAST frames.  16-byte image loads need K % 16 == 0 (28 x 28 = 784 is).
-    // Staging buffers per warp (BSB_IMAGE_STAGES, default 1): the pixel conversion is issue-bound, so resident
-    // warps matter more than overlapping a warp's own fill with its own store -- other warps fill that gap.
+    // mnist through the TMA unit: groups of m tiles staged in shared memory + mz all-zero tiles per CTA for the LAST
+    // frames.  16-byte image loads need K % 16 == 0 (28 x 28 = 784 is).  Defaults (BSB_IMAGE_STAGES, BSB_IMAGE_GROUP):
+    // ONE staging buffer of m = 2 tiles per warp (6 KB) in 128-thread CTAs with mz = 8 zero tiles (25 KB, shared by
+    // the CTA's warps): 50 KB per CTA -> 4 CTAs = 16 warps per SM, the register limit.  The pixel conversion is
+    // issue-bound, so resident warps matter more than overlapping a warp's own fill with its own store (other
+    // warps fill that gap) or than the size of the staged stores; the zero frames still leave in 25 KB stores.
     const int stages = e->image_stages;
-    int m = 4;
+    int m = e->image_group;
     while (m > 1 && (size_t)stages * m * tile > 28 * 1024) m >>= 1;
     if (m > chunk) m = chunk;
+    int mz = 8;
+    while (mz > 1 && ((size_t)mz * tile > 28 * 1024 || mz > chunk)) mz >>= 1;
+    if (mz < m) mz = m;
     if ((K & 15) != 0 || (size_t)stages * m * tile > 64 * 1024) {
       a.emit_bulk = 0;
     } else {
-      a.group_lanes = m; a.stage_rows = stages; threads = 64; a.cta_extra_floats = m * K; persistent = e->deep_sea_persistent != 0;
+      a.group_lanes = m; a.stage_rows = stages; threads = 128; a.cta_extra_floats = mz * K; persistent = e->deep_sea_persistent != 0;
+      if (n_chunks < 2 * (int64_t)e->num_sms) threads = 64;      // small batches: more, smaller CTAs
     }
   }
   a.use_pdl = (e->use_pdl && !a.no_pdl && a.mode == MODE_STEP && a.T == 1) ? 1 : 0;
@@ -160,6 +166,8 @@ int device_launch(bsb_env* e, LaunchArgs a, cudaStream_t stream) {
   auto kernel = transition_kernel<F, RK, kNoise, kTrack>;
   if (smem > 48 * 1024) BSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t grid = (n_chunks + threads / 32 - 1) / (threads / 32);
+  const bool two_phase = a.early_scalars != 0 && a.mailbox != nullptr;
+  if (two_phase) grid += 1;                // block 0 is the signaller of a two-phase host step: it owns no chunks
   if (persistent) {
     // As many CTAs as are co-resident (shared-memory bound; 1 KB per CTA is reserved by the driver); their warps
     // draw chunks from the environment's global counter.

@@ -440,6 +440,7 @@ int32_t bsb_create(const bsb_config* config, int64_t batch, int32_t device, uint
     e->lazy_fetch = flag("BSB_LAZY_FETCH", 1);
     { const char* v = getenv("BSB_L2_HINT"); e->l2_hint = v ? atoi(v) : 1; if (e->l2_hint < 0 || e->l2_hint > 2) e->l2_hint = 1; }
     { const char* v = getenv("BSB_IMAGE_STAGES"); e->image_stages = (v && atoi(v) == 2) ? 2 : 1; }
+    { const char* v = getenv("BSB_IMAGE_GROUP"); const int g = v ? atoi(v) : 2; e->image_group = (g == 1 || g == 4) ? g : 2; }
     { const char* v = getenv("BSB_CHUNK_LANES"); e->chunk_lanes = v ? atoi(v) : 0;
       if (e->chunk_lanes != 8 && e->chunk_lanes != 16 && e->chunk_lanes != 32) e->chunk_lanes = 0; }
     e->work_counter = nullptr; e->work_base = 0;

@@ -51,6 +51,7 @@ struct bsb_env {
   int lazy_fetch;         // persistent kernel: fetch the next chunk lazily (default) or one chunk ahead
   int l2_hint;            // L2 eviction hint of the observation bulk stores (0 none, 1 evict_first, 2 evict_last)
   int image_stages;       // mnist TMA path: staging buffers per warp (1 or 2)
+  int image_group;        // mnist TMA path: tiles per staged store (1, 2 or 4)
   int chunk_lanes;        // lanes per chunk: 0 = automatic (32; 16 / 8 for small mnist batches), BSB_CHUNK_LANES forces
   int num_sms;
   bsb::InfoNames names;

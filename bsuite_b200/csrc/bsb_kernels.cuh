@@ -321,8 +321,11 @@ __device__ __forceinline__ void emit_image(const EnvParams& p, const float* lut,
 // correctly rounded v / 255 for every int8 v: checked exhaustively against numpy on the device
 // (tests/test_round2_features.py) -- 256 inputs, no reasoning about rounding needed.
 __device__ __forceinline__ float pixel_div255(uint32_t word, int byte) {
+  // prmt.b32: bit 3 of a selector nibble replicates the sign of the selected byte (the __byte_perm intrinsic masks
+  // that bit off): byte `byte` in the low byte, its sign in the three bytes above = the sign-extended int8
   const uint32_t sel = (uint32_t)byte | ((8u | (uint32_t)byte) << 4) | ((8u | (uint32_t)byte) << 8) | ((8u | (uint32_t)byte) << 12);
-  const int v = (int)__byte_perm(word, 0u, sel);
+  int v;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(v) : "r"(word), "r"(0u), "r"(sel));
   const float x = __fadd_rn(__int_as_float(0x4B400000 + v), -12582912.0f);
   const float hi = 0.003921568859368563f, lo = -2.319175823606301e-10f;      // float(1/255), float(1/255 - hi)
   return __fmaf_rn(x, hi, __fmul_rn(x, lo));
@@ -331,65 +334,74 @@ __device__ __forceinline__ float4 pixels4(uint32_t w) {
   return make_float4(pixel_div255(w, 0), pixel_div255(w, 1), pixel_div255(w, 2), pixel_div255(w, 3));
 }
 
-// Image tiles through shared memory and the TMA unit (K % 16 == 0, e.g. 28 x 28).  Lanes are taken in groups of
-// `m` (<= 4) consecutive lanes = m contiguous tiles in global memory:
-//   * a group whose lanes all show the all-zero LAST frame (mnist.py:74; every other step of every lane) is ONE
-//     bulk store from the CTA's zero tiles -- nothing is staged, nothing is waited for;
-//   * otherwise all 16-byte loads of the group's int8 images (49 per 28 x 28 tile, <= 8 per thread) are issued
-//     before the first conversion, the float32 tiles land in one of two staging buffers and leave as one bulk
-//     store of m * 4K bytes.
+// Image tiles through shared memory and the TMA unit (K % 16 == 0, e.g. 28 x 28).  The chunk's lanes are walked in
+// blocks of `mz` consecutive lanes (= mz contiguous tiles in global memory):
+//   * a block whose lanes all show the all-zero LAST frame (mnist.py:74; every other step of every lane) is ONE
+//     bulk store of mz tiles (25 KB at mz = 8) from the CTA's zero tiles -- nothing is staged, nothing waited for;
+//   * otherwise the block goes in groups of `m` (<= 4) lanes: all 16-byte loads of the group's int8 images (49 per
+//     28 x 28 tile) are issued before the first conversion, the float32 tiles land in a staging buffer and leave
+//     as one bulk store of m * 4K bytes.
 // stage = [256 floats: table of the vector path][stages x m x K floats]; `emitted` counts staged stores (buffer
-// parity).  stages = 1 halves the shared memory per warp: more resident warps for the conversion.
+// parity).  Small staging buffers (m = 2, one stage: 6 KB per warp) keep 16 warps per SM resident -- the conversion
+// is issue-bound (ncu: 266 warp instructions per tile, 40 % issue utilisation at 8 warps per SM) -- while the
+// zero frames, which are pure bandwidth, still leave in 25 KB stores.
 __device__ __forceinline__ void emit_image_bulk(const EnvParams& p, float* stage, const float* cta_zero, float* obs_t,
-                                                int64_t warp_base, int n_lanes, int K, int image, int m, int l2_hint,
-                                                int stages, unsigned& emitted) {
+                                                int64_t warp_base, int n_lanes, int K, int image, int m, int mz,
+                                                int l2_hint, int stages, unsigned& emitted) {
   constexpr int MAXM = 4;
   const int tid = threadIdx.x & 31;
   float* tiles = stage + 256;
   const int K16 = K >> 4;
   const unsigned showing = __ballot_sync(0xffffffffu, image >= 0);
-  for (int g0 = 0; g0 < n_lanes; g0 += m) {
-    const int in_group = (n_lanes - g0) < m ? (n_lanes - g0) : m;
-    float* dst = obs_t + (warp_base + g0) * (int64_t)K;
-    const uint32_t bytes = (uint32_t)in_group * (uint32_t)K * 4u;
-    if (((showing >> g0) & ((1u << in_group) - 1u)) == 0u) {
-      if (tid == 0) { bulk_store_obs(dst, cta_zero, bytes, l2_hint); bulk_commit(); }
+  for (int z0 = 0; z0 < n_lanes; z0 += mz) {
+    const int in_block = (n_lanes - z0) < mz ? (n_lanes - z0) : mz;
+    const unsigned block_mask = (in_block >= 32 ? 0xffffffffu : ((1u << in_block) - 1u));
+    if (((showing >> z0) & block_mask) == 0u) {
+      if (tid == 0) {
+        bulk_store_obs(obs_t + (warp_base + z0) * (int64_t)K, cta_zero, (uint32_t)in_block * (uint32_t)K * 4u, l2_hint);
+        bulk_commit();
+      }
       continue;
     }
-    float* buf = tiles + (size_t)(stages == 2 ? (emitted & 1u) : 0u) * m * K;
-    // two staging buffers: at most the newest store may still be reading, never this buffer; one: none may
-    if (tid == 0) { if (stages == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
-    __syncwarp();
-    int img[MAXM];
+    for (int g0 = z0; g0 < z0 + in_block; g0 += m) {
+      const int in_group = (z0 + in_block - g0) < m ? (z0 + in_block - g0) : m;
+      float* dst = obs_t + (warp_base + g0) * (int64_t)K;
+      const uint32_t bytes = (uint32_t)in_group * (uint32_t)K * 4u;
+      float* buf = tiles + (size_t)(stages == 2 ? (emitted & 1u) : 0u) * m * K;
+      // two staging buffers: at most the newest store may still be reading, never this buffer; one: none may
+      if (tid == 0) { if (stages == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
+      __syncwarp();
+      int img[MAXM];
 #pragma unroll
-    for (int j = 0; j < MAXM; ++j) img[j] = __shfl_sync(0xffffffffu, image, (g0 + j) & 31);
-    for (int q0 = 0; q0 < K16; q0 += 64) {
-      uint4 c[MAXM][2];
+      for (int j = 0; j < MAXM; ++j) img[j] = __shfl_sync(0xffffffffu, image, (g0 + j) & 31);
+      for (int q0 = 0; q0 < K16; q0 += 64) {
+        uint4 c[MAXM][2];
 #pragma unroll
-      for (int j = 0; j < MAXM; ++j)
+        for (int j = 0; j < MAXM; ++j)
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          const int q = q0 + r * 32 + tid;
-          c[j][r] = make_uint4(0u, 0u, 0u, 0u);
-          if (j < in_group && img[j] >= 0 && q < K16)
-            c[j][r] = __ldg(reinterpret_cast<const uint4*>(p.images + (int64_t)img[j] * K) + q);
-        }
-#pragma unroll
-      for (int j = 0; j < MAXM; ++j)
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          const int q = q0 + r * 32 + tid;
-          if (j < in_group && q < K16) {
-            float4* out = reinterpret_cast<float4*>(buf + (size_t)j * K) + 4 * q;
-            out[0] = pixels4(c[j][r].x); out[1] = pixels4(c[j][r].y);
-            out[2] = pixels4(c[j][r].z); out[3] = pixels4(c[j][r].w);
+          for (int r = 0; r < 2; ++r) {
+            const int q = q0 + r * 32 + tid;
+            c[j][r] = make_uint4(0u, 0u, 0u, 0u);
+            if (j < in_group && img[j] >= 0 && q < K16)
+              c[j][r] = __ldg(reinterpret_cast<const uint4*>(p.images + (int64_t)img[j] * K) + q);
           }
-        }
+#pragma unroll
+        for (int j = 0; j < MAXM; ++j)
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const int q = q0 + r * 32 + tid;
+            if (j < in_group && q < K16) {
+              float4* out = reinterpret_cast<float4*>(buf + (size_t)j * K) + 4 * q;
+              out[0] = pixels4(c[j][r].x); out[1] = pixels4(c[j][r].y);
+              out[2] = pixels4(c[j][r].z); out[3] = pixels4(c[j][r].w);
+            }
+          }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (tid == 0) { bulk_store_obs(dst, buf, bytes, l2_hint); bulk_commit(); }
+      ++emitted;
     }
-    fence_proxy_async_smem();
-    __syncwarp();
-    if (tid == 0) { bulk_store_obs(dst, buf, bytes, l2_hint); bulk_commit(); }
-    ++emitted;
   }
 }
 
@@ -580,13 +592,17 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
   const bool lazy = a.lazy_fetch != 0;
   // The elected lane draws chunk indices [total_warps, n_chunks) from the global counter and broadcasts them
   // with a shuffle; chunk (global warp index) is taken without asking.
-  const int64_t total_warps = (int64_t)gridDim.x * warps_per_cta;
+  // Two-phase host steps set one block aside as the SIGNALLER (block 0; see below): it owns no chunks.
+  const bool two_phase = ObsFromState<F>::value && a.early_scalars && a.mailbox && !cancelled;
+  const unsigned worker_blocks = gridDim.x - (two_phase ? 1u : 0u);
+  const unsigned worker_block = blockIdx.x - (two_phase ? 1u : 0u);
+  const int64_t total_warps = (int64_t)worker_blocks * warps_per_cta;
   auto fetch_chunk = [&]() -> int64_t {
     unsigned long long v = 0;
     if (tid == 0) v = atomicAdd(a.work_counter, 1ull) - a.work_base;      // graph-safe mode: clock + 1, base 0
     return total_warps + (int64_t)__shfl_sync(0xffffffffu, v, 0);
   };
-  int64_t cur_chunk = (int64_t)blockIdx.x * warps_per_cta + warp;
+  int64_t cur_chunk = (int64_t)worker_block * warps_per_cta + warp;
   if (cancelled) {
     // A stood-down launch still owes the chunk counter its share: a launch over C chunks advances it by exactly C.
     if (dynamic && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(a.work_counter, (unsigned long long)n_chunks);
@@ -662,7 +678,8 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
       }
     } else if (kEmit == EMIT_IMAGE) {
       const int image = Descriptor<F>::a(L);
-      if (bulk) emit_image_bulk(p, stage, cta_zero, obs_t, warp_base, n_lanes, K, active ? image : -1, a.group_lanes, a.l2_hint, a.stage_rows, emitted);
+      if (bulk) emit_image_bulk(p, stage, cta_zero, obs_t, warp_base, n_lanes, K, active ? image : -1, a.group_lanes,
+                                a.cta_extra_floats / K, a.l2_hint, a.stage_rows, emitted);
       else emit_image(p, stage, obs_t, warp_base, n_lanes, K, image, vec && (K & 3) == 0);
     } else if (!a.stage_rows) {
       // observation rows too long for a shared-memory stage: every thread renders its row in place
@@ -695,58 +712,82 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
 
   // ---- two-phase host step (a.early_scalars; families whose observation is a function of the stored state) ----
   // A host-driven step (bsb_step_host) returns when reward / discount / step_type are in host memory; the
-  // observation stays on the device.  So the transitions of ALL chunks run first (phase 1: a few microseconds,
-  // statically dealt), the host is signalled, and the observations are streamed afterwards (phase 2, dynamically
-  // dealt as usual) while the host already decides the next action.  Phase 2 re-reads the lane state phase 1
-  // stored (L2-resident) and renders from it; a warp's first chunk stays in registers.
+  // observation stays on the device.  So the transitions of ALL chunks run first (phase 1: statically dealt; the
+  // actions of a warp's chunks are fetched over PCIe in one round trip), and the observations are streamed
+  // afterwards (phase 2, dynamically dealt as usual) while the host already decides the next action.  Phase 2
+  // re-reads the lane state phase 1 stored (L2-resident) and renders from it; a warp's first chunk stays in
+  // registers.
+  // Who tells the host?  Not the workers: a system-scope fence waits until the PCIe link has drained every posted
+  // write ahead of it (768 KB of scalars per step: ~13 us), and the workers have 268 MB of observations to issue.
+  // Each worker block only fences at GPU scope and counts itself out in device memory; block 0, the SIGNALLER,
+  // owns no chunks, waits for that count, and issues the one system fence and the completion word.  (PTX memory
+  // model: the workers' release / the signaller's acquire at gpu scope, then fence.sc.sys, make the completion
+  // word causally later than every worker's host writes for the host's acquire load.)
   if constexpr (ObsFromState<F>::value) {
-    if (a.early_scalars && a.mailbox && !cancelled) {
-      const int64_t own = (int64_t)blockIdx.x * warps_per_cta + warp;
-      typename F::Lane keep;
-      F::init(p, keep);
-      for (int64_t c = own; c < n_chunks; c += total_warps) {
-        const int64_t warp_base = c * cl;
-        const int n_lanes = (B - warp_base) < cl ? (int)(B - warp_base) : cl;
-        const int64_t lane = warp_base + tid;
-        typename F::Lane L;
-        F::init(p, L);
-        if (tid < n_lanes) {
-          R rng, wrng;
-          EpisodeStats ep;
-          F::load(p, lane, L);
-          if (has_rng) rng_open(rng, p, lane, false);
-          if (kNoise) rng_open(wrng, p, lane, true);
-          if (kTrack) ep.load(p, lane);
-          int32_t action = __ldcv(io.actions + lane);
-          if ((uint32_t)action >= (uint32_t)p.num_actions) {
-            if (a.bad_action) *a.bad_action = 1;
-            action = action < 0 ? 0 : p.num_actions - 1;
-          }
-          const bool after_last = L.nr != 0;
-          const StepOut o = lane_transition<F, R, R>(p, lane, L, rng, wrng, action, MODE_STEP, kNoise);
-          F::store(p, lane, L);
-          if (has_rng) rng_close(rng, p, lane, false);
-          if (kNoise) rng_close(wrng, p, lane, true);
-          if (kTrack) {
-            ep.track(p, lane, o, step0, after_last);
-            ep.store(p, lane);
-            if (p.log_rows && o.step_type == LAST && log_row_due(p, lane)) log_row_write(p, lane, step0 + 1);
-          }
-          if (io.reward) io.reward[lane] = (float)o.reward;
-          if (io.reward_f64) io.reward_f64[lane] = o.reward;
-          if (io.discount) io.discount[lane] = o.discount;
-          if (io.step_type) io.step_type[lane] = o.step_type;
-        }
-        if (c == own) keep = L;
-      }
-      __threadfence_system();                // scalars (host memory) and lane state (device memory) are out ...
-      __syncthreads();
-      if (threadIdx.x == 0 && atomicAdd(&a.mail->finished, 1ull) == (unsigned long long)gridDim.x - 1ull) {
+    if (two_phase && blockIdx.x == 0) {
+      if (threadIdx.x == 0) {
+        while (*reinterpret_cast<volatile unsigned long long*>(&a.mail->finished) < (unsigned long long)worker_blocks) {}
+        __threadfence();
         a.mail->finished = 0ull;
-        a.mail->phase1 = a.ticket;           // ... for every chunk: phase 2 may read any lane's state now
+        a.mail->phase1 = a.ticket;           // every chunk's state is stored: phase 2 may read any lane's state now
         __threadfence_system();
         st_sys_u64(&a.mailbox->done, a.ticket);      // and the host may read its scalars
       }
+      cur_chunk = n_chunks;                  // the signaller owns no chunks
+    } else if (two_phase) {
+      const int64_t own = cur_chunk;
+      typename F::Lane keep;
+      F::init(p, keep);
+      constexpr int kAhead = 8;              // chunks whose actions are in flight together
+      for (int64_t c0 = own; c0 < n_chunks; c0 += kAhead * total_warps) {
+        int32_t fetched[kAhead];
+#pragma unroll
+        for (int k = 0; k < kAhead; ++k) {
+          const int64_t lane = (c0 + k * total_warps) * cl + tid;
+          fetched[k] = (c0 + k * total_warps < n_chunks && lane < B && tid < cl) ? __ldcv(io.actions + lane) : 0;
+        }
+#pragma unroll
+        for (int k = 0; k < kAhead; ++k) {
+          const int64_t c = c0 + k * total_warps;
+          if (c >= n_chunks) break;
+          const int64_t warp_base = c * cl;
+          const int n_lanes = (B - warp_base) < cl ? (int)(B - warp_base) : cl;
+          const int64_t lane = warp_base + tid;
+          typename F::Lane L;
+          F::init(p, L);
+          if (tid < n_lanes) {
+            R rng, wrng;
+            EpisodeStats ep;
+            F::load(p, lane, L);
+            if (has_rng) rng_open(rng, p, lane, false);
+            if (kNoise) rng_open(wrng, p, lane, true);
+            if (kTrack) ep.load(p, lane);
+            int32_t action = fetched[k];
+            if ((uint32_t)action >= (uint32_t)p.num_actions) {
+              if (a.bad_action) *a.bad_action = 1;
+              action = action < 0 ? 0 : p.num_actions - 1;
+            }
+            const bool after_last = L.nr != 0;
+            const StepOut o = lane_transition<F, R, R>(p, lane, L, rng, wrng, action, MODE_STEP, kNoise);
+            F::store(p, lane, L);
+            if (has_rng) rng_close(rng, p, lane, false);
+            if (kNoise) rng_close(wrng, p, lane, true);
+            if (kTrack) {
+              ep.track(p, lane, o, step0, after_last);
+              ep.store(p, lane);
+              if (p.log_rows && o.step_type == LAST && log_row_due(p, lane)) log_row_write(p, lane, step0 + 1);
+            }
+            if (io.reward) io.reward[lane] = (float)o.reward;
+            if (io.reward_f64) io.reward_f64[lane] = o.reward;
+            if (io.discount) io.discount[lane] = o.discount;
+            if (io.step_type) io.step_type[lane] = o.step_type;
+          }
+          if (c == own) keep = L;
+        }
+      }
+      __threadfence();                       // gpu scope: cheap next to a system fence; the signaller does that one
+      __syncthreads();
+      if (threadIdx.x == 0) atomicAdd(&a.mail->finished, 1ull);
       bool mine = true;
       int64_t c = own;
       while (c < n_chunks) {
@@ -857,8 +898,7 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
     // observations are in device memory, so there the stores themselves must have completed
     if (a.mailbox && !a.early_scalars) bulk_wait_all(); else bulk_wait_read<0>();
   }
-  const bool signalled_early = ObsFromState<F>::value && a.early_scalars && !cancelled;
-  if (a.mailbox && !signalled_early) {
+  if (a.mailbox && !two_phase) {
     __threadfence_system();                  // every thread: its zero-copy outputs are visible to the host ...
     __syncthreads();                         // ... before the CTA counts itself finished
     if (threadIdx.x == 0) {
@@ -876,7 +916,9 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
       const unsigned g = blockIdx.x % groups;
       const unsigned members = gridDim.x / groups + (g < gridDim.x % groups ? 1u : 0u);
       unsigned long long* sub = a.clock + CLOCK_SUB0 + 16 * g;
-      __threadfence();
+      // No fence: the count only says "this CTA has READ the step count and drawn its chunks" -- both happened
+      // (their values were consumed) long before; the state it wrote reaches the next launch through the kernel
+      // boundary.  A membar here kept every CTA alive ~1 us longer: +2..7 us per launch on multi-wave grids.
       if (atomicAdd(sub, 1ull) == (unsigned long long)members - 1ull) {
         *sub = 0ull;                          // re-armed for the next launch (which starts after this one ends)
         if (atomicAdd(a.clock + CLOCK_TOP, 1ull) == (unsigned long long)groups - 1ull) {
