@@ -103,6 +103,9 @@ int device_launch(bsb_env* e, LaunchArgs a, cudaStream_t stream) {
   // ~14 KB of shared memory.  umbrella_distract (103-float rows, 13 KB per stage) ran 7 warps per SM with two
   // stages (profiles/r02a_family_ncu_metrics.csv) and is bound by integer-multiply latency, not by the store.
   a.stage_rows = ((size_t)2 * 32 * (size_t)K * sizeof(float) <= 14 * 1024) ? 2 : 1;
+  // A single-step launch gives every warp exactly one row block to emit: the second stage would only be zeroed
+  // (catch) and hold shared memory that another CTA could use.
+  if (a.T == 1 && (EmitKind<F>::value == EMIT_ROWS || EmitKind<F>::value == EMIT_TWOHOT)) a.stage_rows = 1;
   a.cta_extra_floats = 0;
   a.bad_action = e->bad_action_dev;
   // Lanes per chunk.  The image emitter walks the chunk's lanes a few 3 KB tiles at a time, so it is bound by how

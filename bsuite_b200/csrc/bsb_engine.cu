@@ -296,6 +296,8 @@ void destroy_env(bsb_env* e) {
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->order_event) cudaEventDestroy(e->order_event);
     if (e->fence_event) cudaEventDestroy(e->fence_event);
+    if (e->h2d_event) cudaEventDestroy(e->h2d_event);
+    if (e->h2d_stream) cudaStreamDestroy(e->h2d_stream);
     if (e->bad_action_host) cudaFreeHost(e->bad_action_host);
     if (e->mailbox) cudaFreeHost(e->mailbox);
     if (e->mail) cudaFree(e->mail);
@@ -440,7 +442,7 @@ int32_t bsb_create(const bsb_config* config, int64_t batch, int32_t device, uint
     e->lazy_fetch = flag("BSB_LAZY_FETCH", 1);
     { const char* v = getenv("BSB_L2_HINT"); e->l2_hint = v ? atoi(v) : 1; if (e->l2_hint < 0 || e->l2_hint > 2) e->l2_hint = 1; }
     { const char* v = getenv("BSB_IMAGE_STAGES"); e->image_stages = (v && atoi(v) == 2) ? 2 : 1; }
-    { const char* v = getenv("BSB_IMAGE_GROUP"); const int g = v ? atoi(v) : 2; e->image_group = (g == 1 || g == 4) ? g : 2; }
+    { const char* v = getenv("BSB_IMAGE_GROUP"); const int g = v ? atoi(v) : 4; e->image_group = (g == 1 || g == 2) ? g : 4; }
     { const char* v = getenv("BSB_CHUNK_LANES"); e->chunk_lanes = v ? atoi(v) : 0;
       if (e->chunk_lanes != 8 && e->chunk_lanes != 16 && e->chunk_lanes != 32) e->chunk_lanes = 0; }
     e->work_counter = nullptr; e->work_base = 0;
@@ -452,6 +454,8 @@ int32_t bsb_create(const bsb_config* config, int64_t batch, int32_t device, uint
   { const char* v = getenv("BSB_DOORBELL_TIMEOUT_MS"); const long ms = v ? atol(v) : 200; e->doorbell_timeout_ns = (unsigned long long)(ms > 0 ? ms : 200) * 1000000ull; }
   { const char* v = getenv("BSB_HOST_SPIN"); e->host_spin = v ? (atoi(v) != 0) : 1; }
   { const char* v = getenv("BSB_HOST_EARLY"); e->host_early = v ? (atoi(v) != 0) : 1; }
+  { const char* v = getenv("BSB_HOST_STAGE_ACTIONS"); e->host_stage_actions = v ? (atoi(v) != 0) : 1; }
+  e->h2d_stream = nullptr; e->h2d_event = nullptr;
   e->early_inflight = false;
   e->h2d_actions = nullptr; e->d_reward = nullptr; e->d_reward64 = nullptr; e->d_discount = nullptr; e->d_step_type = nullptr; e->d_obs = nullptr;
   e->copy_stream = nullptr;
@@ -920,6 +924,22 @@ int32_t bsb_step_host(bsb_env* env, const int32_t* actions, const bsb_outputs* h
           env->mailbox->doorbell = ticket;
         } else {
           ticket = ++env->next_ticket;
+          if (env->host_stage_actions && env->host_early && family_obs_from_state(env)) {
+            // Two-phase step: phase 1 (the transitions of every lane) is all that stands between this launch and the
+            // observation stream, and reading 4 B per lane over PCIe from inside the kernel is most of it.  The DMA
+            // engine brings the actions over NOW, on a side stream, while the previous step's kernel is still
+            // streaming observations; the launch waits for that copy on the device.  (The previous kernel read its
+            // actions in phase 1, which ended before its completion word was seen: the buffer is free.)
+            if (!env->h2d_actions) BSB_CUDA(cudaMalloc(&env->h2d_actions, B * 4));
+            if (!env->h2d_stream) {
+              BSB_CUDA(cudaStreamCreateWithFlags(&env->h2d_stream, cudaStreamNonBlocking));
+              BSB_CUDA(cudaEventCreateWithFlags(&env->h2d_event, cudaEventDisableTiming));
+            }
+            BSB_CUDA(cudaMemcpyAsync(env->h2d_actions, actions, B * 4, cudaMemcpyHostToDevice, env->h2d_stream));
+            BSB_CUDA(cudaEventRecord(env->h2d_event, env->h2d_stream));
+            BSB_CUDA(cudaStreamWaitEvent(zs, env->h2d_event, 0));
+            f.actions = env->h2d_actions;
+          }
           int lrc = mailbox_launch(env, ticket, env->steps_done, &f, false);
           if (lrc != BSB_OK) return lrc;
         }

@@ -738,30 +738,36 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
       const int64_t own = cur_chunk;
       typename F::Lane keep;
       F::init(p, keep);
-      constexpr int kAhead = 8;              // chunks whose actions are in flight together
+      constexpr int kAhead = 4;              // chunks whose loads (action, lane state, accumulators) are in flight together
       for (int64_t c0 = own; c0 < n_chunks; c0 += kAhead * total_warps) {
+        // every independent load of up to kAhead chunks first: one round trip to L2 (or over PCIe, when the actions
+        // were not staged on the device) instead of one per chunk -- a warp owns 4-5 chunks of a 65 536-lane batch
         int32_t fetched[kAhead];
+        typename F::Lane lanes[kAhead];
+        EpisodeStats eps[kAhead];
 #pragma unroll
         for (int k = 0; k < kAhead; ++k) {
-          const int64_t lane = (c0 + k * total_warps) * cl + tid;
-          fetched[k] = (c0 + k * total_warps < n_chunks && lane < B && tid < cl) ? __ldcv(io.actions + lane) : 0;
+          const int64_t c = c0 + k * total_warps;
+          const int64_t lane = c * cl + tid;
+          const bool live = c < n_chunks && tid < cl && lane < B;
+          fetched[k] = 0;
+          F::init(p, lanes[k]);
+          if (live) {
+            fetched[k] = __ldcv(io.actions + lane);
+            F::load(p, lane, lanes[k]);
+            if (kTrack) eps[k].load(p, lane);
+          }
         }
 #pragma unroll
         for (int k = 0; k < kAhead; ++k) {
           const int64_t c = c0 + k * total_warps;
           if (c >= n_chunks) break;
-          const int64_t warp_base = c * cl;
-          const int n_lanes = (B - warp_base) < cl ? (int)(B - warp_base) : cl;
-          const int64_t lane = warp_base + tid;
-          typename F::Lane L;
-          F::init(p, L);
-          if (tid < n_lanes) {
+          const int64_t lane = c * cl + tid;
+          typename F::Lane& L = lanes[k];
+          if (tid < cl && lane < B) {
             R rng, wrng;
-            EpisodeStats ep;
-            F::load(p, lane, L);
             if (has_rng) rng_open(rng, p, lane, false);
             if (kNoise) rng_open(wrng, p, lane, true);
-            if (kTrack) ep.load(p, lane);
             int32_t action = fetched[k];
             if ((uint32_t)action >= (uint32_t)p.num_actions) {
               if (a.bad_action) *a.bad_action = 1;
@@ -773,8 +779,8 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
             if (has_rng) rng_close(rng, p, lane, false);
             if (kNoise) rng_close(wrng, p, lane, true);
             if (kTrack) {
-              ep.track(p, lane, o, step0, after_last);
-              ep.store(p, lane);
+              eps[k].track(p, lane, o, step0, after_last);
+              eps[k].store(p, lane);
               if (p.log_rows && o.step_type == LAST && log_row_due(p, lane)) log_row_write(p, lane, step0 + 1);
             }
             if (io.reward) io.reward[lane] = (float)o.reward;
