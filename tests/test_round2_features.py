@@ -238,3 +238,22 @@ def test_observations_too_long_for_the_shared_memory_stage_fall_back(env_class, 
     np.testing.assert_array_equal(_np(getattr(got, field)), _np(getattr(want, field)), err_msg=field)
   one = dev.step(actions[0].cuda())
   np.testing.assert_array_equal(_np(one.observation), _np(host.step(actions[0]).observation))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('bsuite_id,batch', [('catch/0', 1003), ('deep_sea/3', 77), ('deep_sea/11', 30001)])
+def test_two_phase_host_steps_with_ragged_batches_and_float64_rewards(bsuite_id, batch):
+  """Two-phase host steps (scalars staged on the device, shipped by copier blocks): batch sizes that leave the
+  staging arrays unaligned, a ragged last chunk, the persistent grid (30 001 lanes), float64 rewards."""
+  a = bsuite_b200.load_from_id(bsuite_id, batch=batch, device='cuda', seed=9, track_episodes=True, reward_dtype='float64')
+  b = bsuite_b200.load_from_id(bsuite_id, batch=batch, device='cuda', seed=9, track_episodes=True, reward_dtype='float64')
+  host = b.make_host_buffers()
+  T = 25
+  actions = torch.as_tensor(np.random.RandomState(1).randint(a.num_actions, size=(T, batch)).astype(np.int32)).pin_memory()
+  for t in range(T):
+    want = a.step(actions[t].cuda())
+    got, obs = b.step_host(actions[t], host)
+    for field in ('step_type', 'reward', 'discount'):
+      np.testing.assert_array_equal(_np(getattr(got, field)), _np(getattr(want, field)), err_msg=f'{field} t={t}')
+    assert torch.equal(obs, want.observation), t
+  np.testing.assert_array_equal(a.state_dict()['blob'], b.state_dict()['blob'])
