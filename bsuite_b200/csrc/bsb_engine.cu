@@ -233,19 +233,8 @@ int mailbox_launch(bsb_env* e, unsigned long long ticket, int64_t step0, const M
   a.T = 1; a.step0 = step0; a.mode = MODE_STEP;
   a.mailbox = e->mailbox_dev; a.mail = e->mail; a.ticket = ticket; a.wait_doorbell = wait_doorbell ? 1 : 0;
   a.doorbell_timeout_ns = e->doorbell_timeout_ns;
-  a.early_scalars = (e->host_early && family_obs_from_state(e)) ? 1 : 0;      // device_launch turns it into the copier count
-  if (a.early_scalars) {
-    // device staging of the scalars: reward | discount | step_type in one block (as the staged-copy path keeps them)
-    const size_t B = (size_t)e->p.batch;
-    if (!e->d_reward) {
-      BSB_CUDA(cudaMalloc(&e->d_reward, 3 * B * 4));
-      e->d_discount = e->d_reward + B;
-      e->d_step_type = reinterpret_cast<int32_t*>(e->d_reward + 2 * B);
-    }
-    if (!e->d_reward64) BSB_CUDA(cudaMalloc(&e->d_reward64, B * 8));
-    a.stage.reward = e->d_reward; a.stage.reward_f64 = e->d_reward64; a.stage.discount = e->d_discount; a.stage.step_type = e->d_step_type;
-    e->early_inflight = true;
-  }
+  a.early_scalars = (e->host_early && family_obs_from_state(e)) ? 1 : 0;
+  if (a.early_scalars) e->early_inflight = true;
   return run(e, a, e->copy_stream);
 }
 
