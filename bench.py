@@ -506,10 +506,11 @@ def engine_main(args):
       dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     return world * B * n / _median([float(x) for x in dt]), [world * B * n / float(x) for x in dt]
 
-  # headline: the host-policy loop (prelaunch=True): every call rings the doorbell of a kernel that is already
-  # resident and queues the next one; `launch_per_step_value` is the same call without the pre-launch
-  e2e_value, e2e_windows = timed_e2e(Ke, host_small, WINDOWS, prelaunch=True)
-  e2e_plain, _ = timed_e2e(Ke, host_small, 3, prelaunch=False)
+  # headline: one step_host call per step (two-phase host step: the call returns when the scalars have landed and
+  # launches the next kernel while this one still streams observations); `prelaunch_value` is the same loop with
+  # the next step's kernel queued ahead and rung through the doorbell
+  e2e_value, e2e_windows = timed_e2e(Ke, host_small, WINDOWS, prelaunch=False)
+  e2e_prelaunch, _ = timed_e2e(Ke, host_small, 3, prelaunch=True)
 
   # The same host-memory traffic WITHOUT a host synchronise per step (actions that do not depend on the previous
   # result, as in this random-action workload): env.step() given a pinned host action tensor and outputs whose
@@ -642,20 +643,20 @@ def engine_main(args):
                      'launch_us': launch_s * 1e6, 'kernel': KERNEL_NAME},
         'cpu_baseline': cpu_baseline,
         'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 4 * B, 'd2h_bytes_per_step': 12 * B,
-                'steps': Ke, 'windows': e2e_windows, 'launch_per_step_value': e2e_plain,
+                'steps': Ke, 'windows': e2e_windows, 'prelaunch_value': e2e_prelaunch,
                 'host_obs_value': host_obs_value, 'pipelined_value': e2e_pipelined,
                 'host_obs_d2h_bytes_per_step': 4 * B * SIZE * SIZE + 12 * B,
-                'note': 'BatchedEnvironment.step_host(prelaunch=True) -> bsb_step_host(BSB_HOST_PRELAUNCH) every step, the '
-                        'call pattern of a host-side policy: actions come from pinned host memory and reward / discount / '
-                        'step_type land in pinned host memory (read / written in place over PCIe by the kernel: '
-                        'zero-copy); each call hands the buffers to a kernel that is already resident (doorbell in pinned '
-                        'memory), queues the next step\'s kernel and returns when this step\'s results have landed '
-                        '(completion word in pinned memory, no stream synchronise); observations stay on the device '
-                        '(the API contract). launch_per_step_value: the same call without the pre-launch (one kernel '
-                        'launch per call, completion through the mailbox). host_obs_value also copies the observations '
-                        'to pinned host memory every step. pipelined_value: the same per-step host traffic through '
-                        'env.step() with pinned actions and pinned scalar outputs, launches queued, one synchronise at '
-                        'the end.'},
+                'note': 'BatchedEnvironment.step_host -> bsb_step_host every step, the call pattern of a host-side policy: '
+                        'actions come from pinned host memory (brought over by the DMA engine on a side stream while the '
+                        'previous kernel still streams observations) and reward / discount / step_type land in pinned '
+                        'host memory; deep_sea runs the step in two phases -- transitions of all lanes into a device '
+                        'staging block, which copier blocks ship to the host while the others stream the observations -- '
+                        'and the call returns when the scalars have landed (completion word in pinned memory, no stream '
+                        'synchronise); observations stay on the device (the API contract; the caller\'s stream is fenced '
+                        'behind them). prelaunch_value: the same loop with the next step\'s kernel queued ahead and '
+                        'waiting on a doorbell in pinned memory. host_obs_value also copies the observations to pinned '
+                        'host memory every step. pipelined_value: the same per-step host traffic through env.step() with '
+                        'pinned actions and pinned scalar outputs, launches queued, one synchronise at the end.'},
         'gpu_launches': int(launches),
         'fused_rollout': fused,
         'graph_replay': graph_replay,
