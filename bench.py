@@ -299,7 +299,10 @@ def family_leg(name, ids, lanes, rank, world, device, torch, dist, peak_gbs, rol
   batch.set_ring(1 if T * obs_bytes > 300e6 else ring)
   roll_s = timed(T, max(3, iters // T))
   # the same lock-step captured ONCE into a CUDA graph (every id's launch on its own branch) and replayed
-  graphed = batch.capture(1, lock_steps=ring)
+  try:
+    graphed = batch.capture(1, lock_steps=ring)
+  except Exception as exc:  # pylint: disable=broad-except  (deterministic per configuration: every rank takes this branch)
+    graphed, graph_error = None, repr(exc)[:200]
   def timed_graph(n, windows=3):
     times = []
     for _ in range(3):
@@ -324,7 +327,7 @@ def family_leg(name, ids, lanes, rank, world, device, torch, dist, peak_gbs, rol
     if world > 1:
       dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return _median([float(x) for x in t]) * 1e-3 / (n * ring)
-  graph_s = timed_graph(max(3, iters // ring))
+  graph_s = timed_graph(max(3, iters // ring)) if graphed is not None else float('nan')
   del graphed
   total_lanes = len(ids) * lanes
   result = {
