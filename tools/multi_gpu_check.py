@@ -47,7 +47,10 @@ def main():
     got_async = async_lp.result(ticket)[..., :3]
     got_native = native_lp.result()[..., :3]
     torch.cuda.synchronize()
-    ok = ok and torch.equal(got_async, sync) and torch.equal(got_native, sync)
+    a_ok, n_ok = torch.equal(got_async, sync), torch.equal(got_native, sync)
+    if not (a_ok and n_ok):
+      print(f'[rank {rank}] round {round_}: async==sync {a_ok}, native==sync {n_ok}\n sync {sync.tolist()}\n async {got_async.tolist()}\n native {got_native.tolist()}', flush=True)
+    ok = ok and a_ok and n_ok
   # sharding invariance: rank 0 also runs the whole batch and compares its own slice and the gathered totals
   totals = async_lp.result(async_lp.issue(), host_sync=True).sum(dim=0)     # [n_envs, 5]
   if rank == 0:
@@ -58,6 +61,8 @@ def main():
         whole.rollout(3, action_seed=100 + round_)
       want = whole.episode_stat_sums()
       same = torch.allclose(totals[k], want, rtol=0, atol=1e-6 if bsuite_id.startswith('cartpole') else 0)
+      if not same:
+        print(f'[rank 0] sharding: {bsuite_id}: sharded totals {totals[k].tolist()} vs whole {want.tolist()}', flush=True)
       ok = ok and bool(same)
       whole.close()
   flag = torch.tensor([1.0 if ok else 0.0], device=device)
