@@ -60,7 +60,8 @@ def main():
         whole.rollout(T, action_seed=round_)
         whole.rollout(3, action_seed=100 + round_)
       want = whole.episode_stat_sums()
-      same = torch.allclose(totals[k], want, rtol=0, atol=1e-6 if bsuite_id.startswith('cartpole') else 0)
+      # sums over lanes of float rewards depend on the partition in the last bits; the per-lane values do not
+      same = torch.allclose(totals[k], want, rtol=1e-12, atol=1e-6 if bsuite_id.startswith('cartpole') else 1e-9)
       if not same:
         print(f'[rank 0] sharding: {bsuite_id}: sharded totals {totals[k].tolist()} vs whole {want.tolist()}', flush=True)
       ok = ok and bool(same)
