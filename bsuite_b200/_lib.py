@@ -93,6 +93,7 @@ EXPORTS = {
     'bsb_step_host': (ctypes.c_int32, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(Outputs), ctypes.c_void_p,
                                        ctypes.c_void_p, ctypes.c_uint32]),
     'bsb_host_flush': (ctypes.c_int32, [ctypes.c_void_p]),
+    'bsb_host_timing': (ctypes.c_int32, [ctypes.c_void_p, ctypes.c_void_p]),
     'bsb_invalid_actions': (ctypes.c_int32, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32)]),
     'bsb_comm_unique_id': (ctypes.c_int32, [ctypes.c_void_p]),
     'bsb_comm_create': (ctypes.c_int32, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,

@@ -233,6 +233,7 @@ int mailbox_launch(bsb_env* e, unsigned long long ticket, int64_t step0, const M
   a.T = 1; a.step0 = step0; a.mode = MODE_STEP;
   a.mailbox = e->mailbox_dev; a.mail = e->mail; a.ticket = ticket; a.wait_doorbell = wait_doorbell ? 1 : 0;
   a.doorbell_timeout_ns = e->doorbell_timeout_ns;
+  { static const int timing = getenv("BSB_HOST_TIMING") ? atoi(getenv("BSB_HOST_TIMING")) : 0; a.timing = timing; }
   a.early_scalars = (e->host_early && family_obs_from_state(e)) ? 1 : 0;
   if (a.early_scalars) e->early_inflight = true;
   return run(e, a, e->copy_stream);
@@ -826,6 +827,13 @@ int32_t bsb_invalid_actions(bsb_env* env, int32_t* seen) {
   if (!env || !seen) return fail(BSB_INVALID_ARGUMENT, "null argument");
   *seen = 0;
   if (env->bad_action_host) { *seen = *env->bad_action_host; *env->bad_action_host = 0; }
+  return BSB_OK;
+}
+
+int32_t bsb_host_timing(bsb_env* env, uint64_t* stamps8) {
+  if (!env || !stamps8) return fail(BSB_INVALID_ARGUMENT, "null argument");
+  if (!env->mailbox) return fail(BSB_INVALID_ARGUMENT, "no host-driven step has run on this handle");
+  for (int k = 0; k < 8; ++k) stamps8[k] = env->mailbox->stamp[k];
   return BSB_OK;
 }
 

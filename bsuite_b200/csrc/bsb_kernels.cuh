@@ -71,6 +71,7 @@ struct LaunchArgs {
   struct DeviceMail* mail;           // device memory: doorbell relay + finished-CTA counter
   unsigned long long ticket;
   int32_t early_scalars;             // 1: two-phase host step -- signal the host when the scalars of every lane are out
+  int32_t timing;                    // BSB_HOST_TIMING: leave %globaltimer stamps in the mailbox
   int32_t wait_doorbell;             // 1: pre-launched -- poll the doorbell for `ticket`, then take the buffers from the mailbox
   unsigned long long doorbell_timeout_ns;
   int32_t* bad_action;      // pinned host flag (device alias): set to 1 when an action is outside [0, num_actions)
@@ -90,10 +91,15 @@ struct HostMailbox {
   MailFields in;                          // words 1..7 of the same 64-byte line
   unsigned long long pad0[8];
   volatile unsigned long long done;     unsigned long long pad1[7];     // device -> host, a line of its own
+  // BSB_HOST_TIMING=1 (tools/e2e_timeline.py): %globaltimer stamps of the latest two-phase launch, written by its
+  // signaller before `done`: [0] block 0 past the dependency wait, [1] phase 1 complete on every block, [2] just
+  // before `done`, [3] the latest exit of any block of the PREVIOUS launch
+  volatile unsigned long long stamp[8];
 };
 static_assert(sizeof(MailFields) == 56, "doorbell + fields must fill exactly one 64-byte line");
 struct DeviceMail {
   volatile unsigned long long relay;      // ticket (| MAIL_CANCEL) most recently taken from the host doorbell
+  unsigned long long last_exit;           // BSB_HOST_TIMING: max %globaltimer at which a block of the latest launch left
   unsigned long long finished;            // blocks of the current launch that have finished (phase 1, if two-phase)
   volatile unsigned long long phase1;     // ticket of the latest two-phase launch whose phase 1 is complete
   MailFields in;                          // the host's fields, copied once per launch by block 0
@@ -726,11 +732,18 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
   if constexpr (ObsFromState<F>::value) {
     if (two_phase && blockIdx.x == 0) {
       if (threadIdx.x == 0) {
+        const unsigned long long t_start = a.timing ? global_timer_ns() : 0ull;
         while (*reinterpret_cast<volatile unsigned long long*>(&a.mail->finished) < (unsigned long long)worker_blocks) {}
         __threadfence();
         a.mail->finished = 0ull;
         a.mail->phase1 = a.ticket;           // every chunk's state is stored: phase 2 may read any lane's state now
+        if (a.timing) {
+          st_sys_u64(&a.mailbox->stamp[0], t_start);
+          st_sys_u64(&a.mailbox->stamp[1], global_timer_ns());
+          st_sys_u64(&a.mailbox->stamp[3], a.mail->last_exit);
+        }
         __threadfence_system();
+        if (a.timing) st_sys_u64(&a.mailbox->stamp[2], global_timer_ns());
         st_sys_u64(&a.mailbox->done, a.ticket);      // and the host may read its scalars
       }
       cur_chunk = n_chunks;                  // the signaller owns no chunks
@@ -904,6 +917,7 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
     // observations are in device memory, so there the stores themselves must have completed
     if (a.mailbox && !a.early_scalars) bulk_wait_all(); else bulk_wait_read<0>();
   }
+  if (a.timing && a.mail && threadIdx.x == 0) atomicMax(&a.mail->last_exit, global_timer_ns());
   if (a.mailbox && !two_phase) {
     __threadfence_system();                  // every thread: its zero-copy outputs are visible to the host ...
     __syncthreads();                         // ... before the CTA counts itself finished

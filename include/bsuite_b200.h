@@ -338,6 +338,11 @@ int32_t bsb_step_host(bsb_env* env, const int32_t* actions,
 /* Stands down a launch queued by BSB_HOST_PRELAUNCH (no-op otherwise). */
 int32_t bsb_host_flush(bsb_env* env);
 
+/* Diagnostics (BSB_HOST_TIMING=1): %globaltimer stamps, in ns, the latest two-phase
+ * host step left in the mailbox: [0] kernel past its dependency wait, [1] phase 1
+ * complete, [2] scalars fenced, [3] latest block exit of the previous launch. */
+int32_t bsb_host_timing(bsb_env* env, uint64_t* stamps8);
+
 /*
  * Out-of-range actions.  Host-resident actions (host environments,
  * bsb_step_host) are validated before anything moves.  Device-resident action
