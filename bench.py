@@ -303,7 +303,7 @@ def family_leg(name, ids, lanes, rank, world, device, torch, dist, peak_gbs, rol
     graphed = batch.capture(1, lock_steps=ring)
   except Exception as exc:  # pylint: disable=broad-except  (deterministic per configuration: every rank takes this branch)
     graphed, graph_error = None, repr(exc)[:200]
-  def timed_graph(n, windows=3):
+  def timed_graph(n, per_replay, windows=3):
     times = []
     for _ in range(3):
       graphed.replay()
@@ -326,9 +326,18 @@ def family_leg(name, ids, lanes, rank, world, device, torch, dist, peak_gbs, rol
     t = torch.tensor(times, dtype=torch.float64, device=device)
     if world > 1:
       dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return _median([float(x) for x in t]) * 1e-3 / (n * ring)
-  graph_s = timed_graph(max(3, iters // ring)) if graphed is not None else float('nan')
+    return _median([float(x) for x in t]) * 1e-3 / (n * per_replay)
+  graph_s = timed_graph(max(3, iters // ring), ring) if graphed is not None else float('nan')
   del graphed
+  # the T-fused rollout of every id captured in ONE graph: at a few hundred lanes per id and GPU the eager rollout
+  # is bound by the 23 launches the Python face makes per iteration, not by the GPU
+  graph_roll_s = float('nan')
+  try:
+    graphed = batch.capture(T, lock_steps=1)
+    graph_roll_s = timed_graph(max(3, iters // T), T)
+    del graphed
+  except Exception:  # pylint: disable=broad-except
+    pass
   total_lanes = len(ids) * lanes
   result = {
       'ids': len(ids), 'lanes_per_id': lanes, 'global_lanes': total_lanes, 'lanes_per_gpu': total_lanes // world,
@@ -337,11 +346,14 @@ def family_leg(name, ids, lanes, rank, world, device, torch, dist, peak_gbs, rol
       'graph_step_us': graph_s * 1e6, 'graph_step_value': total_lanes / graph_s,
       'graph_step_frac': bytes_per_lockstep / graph_s / 1e9 / peak_gbs,
       'rollout_T': T, 'rollout_us': roll_s * 1e6, 'rollout_value': total_lanes / roll_s,
+      'graph_rollout_us': graph_roll_s * 1e6, 'graph_rollout_value': total_lanes / graph_roll_s,
+      'graph_rollout_frac': bytes_per_lockstep / graph_roll_s / 1e9 / peak_gbs,
       'frac': bytes_per_lockstep / roll_s / 1e9 / peak_gbs,
       'algorithmic_bytes_per_lockstep_per_gpu': bytes_per_lockstep, 'parity_sampled': bool(parity),
       'gather': bool(gather), 'ring': ring, 'unit': 'env-steps/s',
       'note': 'step: eager single-step launches (one per id, ids on concurrent streams); graph_step: the same lock-step '
-              'replayed from one CUDA graph; rollout: T fused steps per launch with on-device actions; *_frac against '
+              'replayed from one CUDA graph; rollout: T fused steps per launch with on-device actions (graph_rollout: '
+              'all ids\' T-step launches in one graph); *_frac against '
               'hbm_gbs with SURVEY 8d algorithmic bytes; single-step outputs cycle through `ring` buffer sets (> L2), '
               'eagerly and under graph replay (`ring` lock-steps per graph)',
   }
