@@ -170,8 +170,12 @@ int device_launch(bsb_env* e, LaunchArgs a, cudaStream_t stream) {
   auto kernel = transition_kernel<F, RK, kNoise, kTrack>;
   if (smem > 48 * 1024) BSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t grid = (n_chunks + threads / 32 - 1) / (threads / 32);
+  // Two-phase host step: the first blocks are COPIERS (they ship the staged scalars to the host, then join phase 2):
+  // enough of them for ~512 threads, i.e. ~64 KB of 16-byte loads in flight.
   const bool two_phase = a.early_scalars != 0 && a.mailbox != nullptr;
-  if (two_phase) grid += 1;                // block 0 is the signaller of a two-phase host step: it owns no chunks
+  const int copiers = two_phase ? (512 / threads > 1 ? 512 / threads : 1) : 0;
+  a.early_scalars = copiers;
+  grid += copiers;
   if (persistent) {
     // As many CTAs as are co-resident (shared-memory bound; 1 KB per CTA is reserved by the driver); their warps
     // draw chunks from the environment's global counter.
@@ -201,7 +205,7 @@ int device_launch(bsb_env* e, LaunchArgs a, cudaStream_t stream) {
   BSB_CUDA(cudaLaunchKernelEx(&cfg, kernel, e->p, a));
   // chunks [warps, n_chunks) are fetched once each and every warp makes exactly one failing fetch
   // (graph-safe mode: the last CTA zeroes the counter instead)
-  if (a.work_counter && !a.clock) e->work_base += (unsigned long long)n_chunks;
+  if (a.work_counter && !a.clock) e->work_base += (unsigned long long)n_chunks + (unsigned long long)(copiers * (threads / 32));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return BSB_OK;
 }

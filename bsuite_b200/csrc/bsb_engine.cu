@@ -234,8 +234,19 @@ int mailbox_launch(bsb_env* e, unsigned long long ticket, int64_t step0, const M
   a.mailbox = e->mailbox_dev; a.mail = e->mail; a.ticket = ticket; a.wait_doorbell = wait_doorbell ? 1 : 0;
   a.doorbell_timeout_ns = e->doorbell_timeout_ns;
   { static const int timing = getenv("BSB_HOST_TIMING") ? atoi(getenv("BSB_HOST_TIMING")) : 0; a.timing = timing; }
-  a.early_scalars = (e->host_early && family_obs_from_state(e)) ? 1 : 0;
-  if (a.early_scalars) e->early_inflight = true;
+  a.early_scalars = (e->host_early && family_obs_from_state(e)) ? 1 : 0;      // device_launch turns it into the copier count
+  if (a.early_scalars) {
+    // device staging of the scalars: reward | discount | step_type in one block (as the staged-copy path keeps them)
+    const size_t B = (size_t)e->p.batch;
+    if (!e->d_reward) {
+      BSB_CUDA(cudaMalloc(&e->d_reward, 3 * B * 4));
+      e->d_discount = e->d_reward + B;
+      e->d_step_type = reinterpret_cast<int32_t*>(e->d_reward + 2 * B);
+    }
+    if (!e->d_reward64) BSB_CUDA(cudaMalloc(&e->d_reward64, B * 8));
+    a.stage.reward = e->d_reward; a.stage.reward_f64 = e->d_reward64; a.stage.discount = e->d_discount; a.stage.step_type = e->d_step_type;
+    e->early_inflight = true;
+  }
   return run(e, a, e->copy_stream);
 }
 
@@ -468,7 +479,7 @@ int32_t bsb_create(const bsb_config* config, int64_t batch, int32_t device, uint
   { const char* v = getenv("BSB_DOORBELL_TIMEOUT_MS"); const long ms = v ? atol(v) : 200; e->doorbell_timeout_ns = (unsigned long long)(ms > 0 ? ms : 200) * 1000000ull; }
   { const char* v = getenv("BSB_HOST_SPIN"); e->host_spin = v ? (atoi(v) != 0) : 1; }
   { const char* v = getenv("BSB_HOST_EARLY"); e->host_early = v ? (atoi(v) != 0) : 1; }
-  { const char* v = getenv("BSB_HOST_STAGE_ACTIONS"); e->host_stage_actions = v ? (atoi(v) != 0) : 0; }
+  { const char* v = getenv("BSB_HOST_STAGE_ACTIONS"); e->host_stage_actions = v ? (atoi(v) != 0) : 1; }
   e->h2d_stream = nullptr; e->h2d_event = nullptr;
   e->early_inflight = false;
   e->h2d_actions = nullptr; e->d_reward = nullptr; e->d_reward64 = nullptr; e->d_discount = nullptr; e->d_step_type = nullptr; e->d_obs = nullptr;

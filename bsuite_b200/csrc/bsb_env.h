@@ -76,7 +76,7 @@ struct bsb_env {
   int host_spin;                      // BSB_HOST_SPIN (default 1): completion through the mailbox instead of a synchronise
   int host_early;                     // BSB_HOST_EARLY (default 1): two-phase host steps (scalars first) where the family allows
   bool early_inflight;                // a two-phase host step may still be streaming observations on copy_stream
-  int host_stage_actions;             // BSB_HOST_STAGE_ACTIONS (default 0): two-phase steps get their actions by DMA on a side stream instead of reading them in place
+  int host_stage_actions;             // BSB_HOST_STAGE_ACTIONS (default 1): two-phase steps get their actions by DMA on a side stream instead of reading them in place
   cudaStream_t h2d_stream; cudaEvent_t h2d_event;
 };
 

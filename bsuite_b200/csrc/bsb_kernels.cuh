@@ -34,6 +34,12 @@
 
 namespace bsb {
 
+// Caller-owned buffers of one step (launch arguments, or the fields of the host mailbox below).
+struct MailFields {
+  const int32_t* actions; float* obs; float* reward; double* reward_f64; float* discount; int32_t* step_type;
+  int32_t obs_vec_ok, pad;
+};
+
 struct LaunchArgs {
   const int32_t* actions;   // [T,B] or null (sample on device)
   int32_t* actions_out;     // [T,B] or null
@@ -70,7 +76,9 @@ struct LaunchArgs {
                                      // paying a stream synchronise.
   struct DeviceMail* mail;           // device memory: doorbell relay + finished-CTA counter
   unsigned long long ticket;
-  int32_t early_scalars;             // 1: two-phase host step -- signal the host when the scalars of every lane are out
+  int32_t early_scalars;             // > 0: two-phase host step; the value is the number of COPIER blocks (blocks
+                                     // [0, n) own no chunks at first: they ship the scalars to the host, see below)
+  MailFields stage;                  // two-phase: device staging of reward / reward_f64 / discount / step_type
   int32_t timing;                    // BSB_HOST_TIMING: leave %globaltimer stamps in the mailbox
   int32_t wait_doorbell;             // 1: pre-launched -- poll the doorbell for `ticket`, then take the buffers from the mailbox
   unsigned long long doorbell_timeout_ns;
@@ -82,10 +90,6 @@ struct LaunchArgs {
 // other blocks through L2.  The last block to finish stores `done = ticket` after a system-scope fence, so every
 // output written to host memory (reward / discount / step_type, zero-copy) is visible when the host sees it.
 static const unsigned long long MAIL_CANCEL = 1ull << 63;      // doorbell: skip the step; done: the step was skipped
-struct MailFields {
-  const int32_t* actions; float* obs; float* reward; double* reward_f64; float* discount; int32_t* step_type;
-  int32_t obs_vec_ok, pad;
-};
 struct HostMailbox {
   volatile unsigned long long doorbell;   // host -> device, word 0 of the line the device polls
   MailFields in;                          // words 1..7 of the same 64-byte line
@@ -102,6 +106,7 @@ struct DeviceMail {
   unsigned long long last_exit;           // BSB_HOST_TIMING: max %globaltimer at which a block of the latest launch left
   unsigned long long finished;            // blocks of the current launch that have finished (phase 1, if two-phase)
   volatile unsigned long long phase1;     // ticket of the latest two-phase launch whose phase 1 is complete
+  unsigned long long copied;              // copier blocks of the current two-phase launch that have shipped their share
   MailFields in;                          // the host's fields, copied once per launch by block 0
 };
 
@@ -621,10 +626,11 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
   const bool lazy = a.lazy_fetch != 0;
   // The elected lane draws chunk indices [total_warps, n_chunks) from the global counter and broadcasts them
   // with a shuffle; chunk (global warp index) is taken without asking.
-  // Two-phase host steps set one block aside as the SIGNALLER (block 0; see below): it owns no chunks.
-  const bool two_phase = ObsFromState<F>::value && a.early_scalars && a.mailbox && !cancelled;
-  const unsigned worker_blocks = gridDim.x - (two_phase ? 1u : 0u);
-  const unsigned worker_block = blockIdx.x - (two_phase ? 1u : 0u);
+  // Two-phase host steps set the first blocks aside as COPIERS (see below): they own no chunks at first.
+  const bool two_phase = ObsFromState<F>::value && a.early_scalars > 0 && a.mailbox && !cancelled;
+  const unsigned copier_blocks = two_phase ? (unsigned)a.early_scalars : 0u;
+  const unsigned worker_blocks = gridDim.x - copier_blocks;
+  const unsigned worker_block = blockIdx.x - copier_blocks;
   const int64_t total_warps = (int64_t)worker_blocks * warps_per_cta;
   auto fetch_chunk = [&]() -> int64_t {
     unsigned long long v = 0;
@@ -634,7 +640,9 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
   int64_t cur_chunk = (int64_t)worker_block * warps_per_cta + warp;
   if (cancelled) {
     // A stood-down launch still owes the chunk counter its share: a launch over C chunks advances it by exactly C.
-    if (dynamic && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(a.work_counter, (unsigned long long)n_chunks);
+    // (a two-phase launch also owes one failing fetch per copier warp, which the host's arithmetic counts too)
+    if (dynamic && blockIdx.x == 0 && threadIdx.x == 0)
+      atomicAdd(a.work_counter, (unsigned long long)n_chunks + (unsigned long long)(a.early_scalars > 0 ? a.early_scalars * warps_per_cta : 0));
     cur_chunk = n_chunks;
   }
 
@@ -746,30 +754,88 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
   // afterwards (phase 2, dynamically dealt as usual) while the host already decides the next action.  Phase 2
   // re-reads the lane state phase 1 stored (L2-resident) and renders from it; a warp's first chunk stays in
   // registers.
-  // Who tells the host?  Not the workers: a system-scope fence waits until the PCIe link has drained every posted
-  // write ahead of it (768 KB of scalars per step: ~13 us), and the workers have 268 MB of observations to issue.
-  // Each worker block only fences at GPU scope and counts itself out in device memory; block 0, the SIGNALLER,
-  // owns no chunks, waits for that count, and issues the one system fence and the completion word.  (PTX memory
-  // model: the workers' release / the signaller's acquire at gpu scope, then fence.sc.sys, make the completion
-  // word causally later than every worker's host writes for the host's acquire load.)
+  // Who ships the scalars to the host?  Not the workers: 768 KB of posted PCIe writes per step back-pressure the
+  // warps that issue them (GPU timeline, profiles/r02_e2e_timeline.txt: a phase 1 that wrote to host memory took
+  // 13 us instead of ~3, and 25 us when it also read its actions over PCIe), and they have 268 MB of observations
+  // to issue.  The workers write reward / discount / step_type to a DEVICE staging block, fence at GPU scope and
+  // count themselves out.  The first `early_scalars` blocks, the COPIERS, own no chunks at first: they wait for
+  // that count, copy the staging block to the host's pinned buffers with 16-byte stores (16 per thread in flight:
+  // ~128 KB across the copiers, enough for the link), issue the system fence, and the last one stores the completion
+  // word; then they join phase 2 through the chunk counter like everybody else.
+  // (PTX memory model: workers release / copiers acquire at gpu scope; the copiers' own stores, fence.sc.sys and the
+  // completion word are program-ordered; the host's acquire load of the word therefore sees every scalar.)
   if constexpr (ObsFromState<F>::value) {
-    if (two_phase && blockIdx.x == 0) {
+    if (two_phase && blockIdx.x < copier_blocks) {
       if (threadIdx.x == 0) {
         const unsigned long long t_start = a.timing ? global_timer_ns() : 0ull;
         while (*reinterpret_cast<volatile unsigned long long*>(&a.mail->finished) < (unsigned long long)worker_blocks) {}
-        __threadfence();
-        a.mail->finished = 0ull;
-        a.mail->phase1 = a.ticket;           // every chunk's state is stored: phase 2 may read any lane's state now
-        if (a.timing) {
-          st_sys_u64(&a.mailbox->stamp[0], t_start);
-          st_sys_u64(&a.mailbox->stamp[1], global_timer_ns());
-          st_sys_u64(&a.mailbox->stamp[3], a.mail->last_exit);
+        if (blockIdx.x == 0) {
+          a.mail->phase1 = a.ticket;         // every chunk's state is stored: phase 2 may read any lane's state
+          if (a.timing) {
+            st_sys_u64(&a.mailbox->stamp[0], t_start);
+            st_sys_u64(&a.mailbox->stamp[1], global_timer_ns());
+            st_sys_u64(&a.mailbox->stamp[3], a.mail->last_exit);
+          }
         }
+      }
+      __syncthreads();
+      __threadfence();                       // acquire: the staging block is read below
+      const int64_t n_thr = (int64_t)copier_blocks * blockDim.x, me = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+      auto ship = [&](const void* from, void* to, int64_t bytes) {
+        if (!from || !to) return;
+        if ((reinterpret_cast<uintptr_t>(from) | reinterpret_cast<uintptr_t>(to)) & 15) {      // odd batch sizes: words
+          const uint32_t* s32 = reinterpret_cast<const uint32_t*>(from);
+          uint32_t* d32 = reinterpret_cast<uint32_t*>(to);
+          for (int64_t i = me; i < (bytes >> 2); i += n_thr) d32[i] = __ldcg(s32 + i);
+          return;
+        }
+        const uint4* src = reinterpret_cast<const uint4*>(from);
+        uint4* dst = reinterpret_cast<uint4*>(to);
+        const int64_t n16 = bytes >> 4;
+        constexpr int U = 16;     // 16 x 16 B per thread in flight: ~128 KB across the copiers, enough for the PCIe link
+        for (int64_t i0 = me; i0 < n16; i0 += U * n_thr) {
+          uint4 v[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) { const int64_t i = i0 + u * n_thr; if (i < n16) v[u] = __ldcg(src + i); }
+#pragma unroll
+          for (int u = 0; u < U; ++u) { const int64_t i = i0 + u * n_thr; if (i < n16) dst[i] = v[u]; }
+        }
+        const char* tail_src = reinterpret_cast<const char*>(from) + (n16 << 4);
+        char* tail_dst = reinterpret_cast<char*>(to) + (n16 << 4);
+        for (int64_t i = me; i < (bytes & 15); i += n_thr) tail_dst[i] = tail_src[i];
+      };
+      ship(a.stage.reward, io.reward, B * 4);
+      ship(a.stage.reward_f64, io.reward_f64, B * 8);
+      ship(a.stage.discount, io.discount, B * 4);
+      ship(a.stage.step_type, io.step_type, B * 4);
+      __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x == 0 && atomicAdd(&a.mail->copied, 1ull) == (unsigned long long)copier_blocks - 1ull) {
+        a.mail->finished = 0ull;             // every copier is past its wait: re-arm both counts for the next launch
+        a.mail->copied = 0ull;
         __threadfence_system();
         if (a.timing) st_sys_u64(&a.mailbox->stamp[2], global_timer_ns());
-        st_sys_u64(&a.mailbox->done, a.ticket);      // and the host may read its scalars
+        st_sys_u64(&a.mailbox->done, a.ticket);      // the host may read its scalars
       }
-      cur_chunk = n_chunks;                  // the signaller owns no chunks
+      // join phase 2: the copiers own no chunk of their own, the counter deals them the rest
+      cur_chunk = n_chunks;
+      if (dynamic) {
+        typename F::Lane L;
+        int64_t c = fetch_chunk();
+        while (c < n_chunks) {
+          const int64_t warp_base = c * cl;
+          const int n_lanes = (B - warp_base) < cl ? (int)(B - warp_base) : cl;
+          const int64_t lane = warp_base + tid;
+          const bool active = tid < n_lanes;
+          F::init(p, L);
+          if (active) { F::load(p, lane, L); F::describe(p, L); }
+          const bool bulk = chunk_is_bulk(n_lanes);
+          any_bulk = any_bulk || bulk;
+          R unused_rng;
+          emit_obs(L, unused_rng, io.obs, warp_base, n_lanes, lane, active, bulk);
+          c = fetch_chunk();
+        }
+      }
     } else if (two_phase) {
       const int64_t own = cur_chunk;
       typename F::Lane keep;
@@ -819,15 +885,15 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
               eps[k].store(p, lane);
               if (p.log_rows && o.step_type == LAST && log_row_due(p, lane)) log_row_write(p, lane, step0 + 1);
             }
-            if (io.reward) io.reward[lane] = (float)o.reward;
-            if (io.reward_f64) io.reward_f64[lane] = o.reward;
-            if (io.discount) io.discount[lane] = o.discount;
-            if (io.step_type) io.step_type[lane] = o.step_type;
+            if (a.stage.reward) a.stage.reward[lane] = (float)o.reward;
+            if (a.stage.reward_f64) a.stage.reward_f64[lane] = o.reward;
+            if (a.stage.discount) a.stage.discount[lane] = o.discount;
+            if (a.stage.step_type) a.stage.step_type[lane] = o.step_type;
           }
           if (c == own) keep = L;
         }
       }
-      __threadfence();                       // gpu scope: cheap next to a system fence; the signaller does that one
+      __threadfence();                       // gpu scope (device memory only): the copiers do the system-scope one
       __syncthreads();
       if (threadIdx.x == 0) atomicAdd(&a.mail->finished, 1ull);
       bool mine = true;
