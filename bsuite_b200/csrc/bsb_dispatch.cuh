@@ -118,7 +118,6 @@ int device_launch(bsb_env* e, LaunchArgs a, cudaStream_t stream) {
   if (e->chunk_lanes > 0) chunk = e->chunk_lanes;
   a.chunk_lanes = chunk;
   const int64_t n_chunks = (B + chunk - 1) / chunk;
-  e->chunks_per_launch = n_chunks;       // the device clock divides by it (graph-safe mode)
   int threads = e->block_threads;
   bool persistent = false;
   const size_t tile = (size_t)K * 4;

@@ -319,21 +319,8 @@ void destroy_env(bsb_env* e) {
 
 }  // namespace
 
-// Graph-safe mode: the steps advanced since the switch are counted on the device (bsb_kernels.cuh, CLOCK_*) as a
-// sum over 32 counters divided by the chunks per launch.  Warp 0 of the block reads it; everybody gets it.
-__device__ int64_t block_clock_steps(const unsigned long long* clock, int64_t chunks_per_launch) {
-  __shared__ long long steps_since;
-  if ((threadIdx.x >> 5) == 0) {
-    unsigned long long sum_s, sum_l;
-    clock_read_warp(clock, sum_s, sum_l);
-    if (threadIdx.x == 0) steps_since = (long long)sum_s / chunks_per_launch;
-  }
-  __syncthreads();
-  return steps_since;
-}
-
-__global__ void episode_stat_kernel(const EnvParams p, int field, int64_t calls, const unsigned long long* clock, int64_t chunks, double* dst) {
-  if (clock) calls += block_clock_steps(clock, chunks);
+__global__ void episode_stat_kernel(const EnvParams p, int field, int64_t calls, const unsigned long long* clock, double* dst) {
+  if (clock) calls += (int64_t)*clock;      // graph-safe mode: steps since the switch are counted on the device
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < p.batch) dst[i] = episode_stat(p, i, field, calls);
 }
@@ -343,9 +330,9 @@ __global__ void episode_stat_kernel(const EnvParams p, int field, int64_t calls,
 // order and re-arms the ticket.  (No floating-point atomics: the result must not depend on scheduling -- a graph
 // replay and an eager call must agree to the bit.)
 constexpr int kSumBlocks = 64, kSumThreads = 256;
-__global__ void episode_sum_kernel(const EnvParams p, int64_t calls, const unsigned long long* clock, int64_t chunks,
+__global__ void episode_sum_kernel(const EnvParams p, int64_t calls, const unsigned long long* clock,
                                    double* scratch, unsigned long long* ticket, double* dst5) {
-  if (clock) calls += block_clock_steps(clock, chunks);
+  if (clock) calls += (int64_t)*clock;
   __shared__ double partial[5][kSumThreads / 32];
   __shared__ bool is_last;
   double v[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
@@ -381,14 +368,14 @@ __global__ void episode_sum_kernel(const EnvParams p, int64_t calls, const unsig
 // the 23-experiment sweep is one kernel instead of 23.  Each environment keeps its own scratch and ticket, and
 // its sums are combined in block order, so the result equals episode_sum_kernel's bit for bit.
 constexpr int kSumManyMax = 64;
-struct SumJob { const double* ep; int64_t batch; int64_t calls; const unsigned long long* clock; int64_t chunks; double* scratch; };
+struct SumJob { const double* ep; int64_t batch; int64_t calls; const unsigned long long* clock; double* scratch; };
 struct SumJobs { SumJob job[kSumManyMax]; };
 __global__ void episode_sum_many_kernel(const SumJobs jobs, double* dst) {
   const SumJob j = jobs.job[blockIdx.y];
   EnvParams p;
   p.ep = const_cast<double*>(j.ep); p.batch = j.batch;
   int64_t calls = j.calls;
-  if (j.clock) calls += block_clock_steps(j.clock, j.chunks);
+  if (j.clock) calls += (int64_t)*j.clock;
   __shared__ double partial[5][kSumThreads / 32];
   __shared__ bool is_last;
   double v[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
@@ -450,7 +437,7 @@ int32_t bsb_create(const bsb_config* config, int64_t batch, int32_t device, uint
 
   bsb_env* e = new bsb_env();
   memset(&e->p, 0, sizeof(e->p));
-  e->device = device; e->steps_done = 0; e->graph_safe = false; e->chunks_per_launch = 1; e->clock = nullptr; e->sum_scratch = nullptr; e->names = info_names(c.family);
+  e->device = device; e->steps_done = 0; e->graph_safe = false; e->clock = nullptr; e->sum_scratch = nullptr; e->names = info_names(c.family);
   {  // tuning knobs (environment variables, read once per handle)
     auto flag = [](const char* name, int dflt) { const char* v = getenv(name); return v ? (atoi(v) != 0 ? 1 : 0) : dflt; };
     const char* bt = getenv("BSB_BLOCK_THREADS");
@@ -620,12 +607,7 @@ static int current_steps(const bsb_env* env, int64_t* steps) {
     DeviceGuard guard(env->device);
     unsigned long long since = 0;
     BSB_CUDA(cudaDeviceSynchronize());
-    unsigned long long parts[CLOCK_GROUPS];      // the S counter of every group (bsb_kernels.cuh, CLOCK_*)
-    BSB_CUDA(cudaMemcpy2D(parts, sizeof(unsigned long long), env->clock, 16 * sizeof(unsigned long long),
-                          sizeof(unsigned long long), CLOCK_GROUPS, cudaMemcpyDeviceToHost));
-    unsigned long long sum = 0;
-    for (int g = 0; g < CLOCK_GROUPS; ++g) sum += parts[g];
-    since = (unsigned long long)((long long)sum / (long long)env->chunks_per_launch);
+    BSB_CUDA(cudaMemcpy(&since, env->clock, sizeof(since), cudaMemcpyDeviceToHost));
     *steps += (int64_t)since;
   }
   return BSB_OK;
@@ -713,7 +695,7 @@ int32_t bsb_read_episode_stats(bsb_env* env, int32_t field, double* dst, void* s
   const int64_t B = env->p.batch;
   if (env->device >= 0) {
     DeviceGuard guard(env->device);
-    episode_stat_kernel<<<(unsigned)((B + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(env->p, field, env->steps_done, env->graph_safe ? env->clock : nullptr, env->chunks_per_launch, dst);
+    episode_stat_kernel<<<(unsigned)((B + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(env->p, field, env->steps_done, env->graph_safe ? env->clock : nullptr, dst);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     BSB_CUDA(cudaGetLastError());
   } else {
@@ -732,7 +714,7 @@ int32_t bsb_sum_episode_stats(bsb_env* env, double* dst5, void* stream) {
     int64_t blocks = (B + kSumThreads - 1) / kSumThreads;
     if (blocks > kSumBlocks) blocks = kSumBlocks;
     episode_sum_kernel<<<(unsigned)blocks, kSumThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        env->p, env->steps_done, env->graph_safe ? env->clock : nullptr, env->chunks_per_launch, env->sum_scratch,
+        env->p, env->steps_done, env->graph_safe ? env->clock : nullptr, env->sum_scratch,
         reinterpret_cast<unsigned long long*>(env->sum_scratch + kSumBlocks * 5), dst5);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     BSB_CUDA(cudaGetLastError());
@@ -763,8 +745,7 @@ int32_t bsb_sum_episode_stats_many(bsb_env* const* envs, int32_t count, double* 
   for (int32_t k = 0; k < count; ++k) {
     { int frc = drain_host_steps(envs[k]); if (frc != BSB_OK) return frc; }
     jobs.job[k].ep = envs[k]->p.ep; jobs.job[k].batch = envs[k]->p.batch; jobs.job[k].calls = envs[k]->steps_done;
-    jobs.job[k].clock = envs[k]->graph_safe ? envs[k]->clock : nullptr; jobs.job[k].chunks = envs[k]->chunks_per_launch;
-    jobs.job[k].scratch = envs[k]->sum_scratch;
+    jobs.job[k].clock = envs[k]->graph_safe ? envs[k]->clock : nullptr; jobs.job[k].scratch = envs[k]->sum_scratch;
   }
   episode_sum_many_kernel<<<dim3(kSumBlocks, (unsigned)count), kSumThreads, 0, static_cast<cudaStream_t>(stream)>>>(jobs, dst);
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -838,11 +819,9 @@ int32_t bsb_set_state(bsb_env* env, const void* src_host, int64_t nbytes, void* 
     // into the device clock as an offset from that base (two's complement, so it may be "negative").
     const unsigned long long since = (unsigned long long)restored - (unsigned long long)env->steps_done;
     BSB_CUDA(cudaDeviceSynchronize());
-    // group 0 carries the whole offset (times the chunks per launch: the kernels divide the sum by it), the others 0
-    unsigned long long parts[CLOCK_GROUPS];
-    for (int g = 0; g < CLOCK_GROUPS; ++g) parts[g] = 0ull;
-    parts[0] = (unsigned long long)((long long)since * (long long)env->chunks_per_launch);
-    BSB_CUDA(cudaMemcpy2D(env->clock, 16 * sizeof(unsigned long long), parts, sizeof(unsigned long long),
+    unsigned long long replicas[CLOCK_GROUPS];
+    for (int r = 0; r < CLOCK_GROUPS; ++r) replicas[r] = since;
+    BSB_CUDA(cudaMemcpy2D(env->clock, 16 * sizeof(unsigned long long), replicas, sizeof(unsigned long long),
                           sizeof(unsigned long long), CLOCK_GROUPS, cudaMemcpyHostToDevice));
   } else {
     env->steps_done = restored;

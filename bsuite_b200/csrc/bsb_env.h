@@ -35,8 +35,7 @@ struct bsb_env {
   // Graph-safe mode: entered for good when a launch of this handle is first captured into a CUDA graph.  From
   // then on the device clock counts the steps (kernel comment in bsb_kernels.cuh) and steps = steps_done + clock[0].
   bool graph_safe;
-  unsigned long long* clock;         // device, CLOCK_WORDS words: monotonic (steps, launches) sums per chunk group + the chunk counter
-  int64_t chunks_per_launch;         // chunks one launch of this handle covers (set by the first launch; constant afterwards)
+  unsigned long long* clock;         // device, CLOCK_WORDS words: step count (replicated), chunk counter, finished-CTA counters
   double* sum_scratch;               // device: bsb_sum_episode_stats partials [64][5] + the ticket
   // tuning knobs (environment variables, read once per handle)
   int block_threads;      // CTA size of the transition kernel (32 / 64 / 128)

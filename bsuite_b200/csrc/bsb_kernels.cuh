@@ -477,9 +477,10 @@ template <> struct Descriptor<Mnist> {
 // Graph-safe mode (a.clock != null; the handle switches to it for good the first time one of its launches is
 // captured into a CUDA graph): launch arguments are frozen in a graph, so everything that changes from launch to
 // launch lives in device memory instead (layout: CLOCK_* below): the steps this handle has advanced since the
-// switch (step index = a.step0 + that count: the on-device action stream and the Logging columns depend on it) and
-// the base of the chunk counter, both as monotonic sums that every CTA reads at its start and every finished chunk
-// adds to with fire-and-forget reductions -- nothing is reset, nobody has to be the last one out.
+// switch (step index = a.step0 + that count: the on-device action stream and the Logging columns depend on it), the
+// chunk counter, and the count of finished CTAs.  The CTA that finishes last advances the step count by T and
+// zeroes the other two; every CTA reads the step count before it counts itself finished, so the update cannot
+// overtake a reader.
 // Register budget per family (second __launch_bounds__ argument, counted in 128-thread blocks per SM).  The
 // generic kernel is register-hungry (two Philox streams, action stream, accumulators); left alone ptxas takes
 // 160-220 registers and 64-thread CTAs then run at 8 warps/SM, which starves the latency-bound small families.
@@ -506,29 +507,17 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-// Graph-safe mode keeps the step count and the chunk-counter base in device memory, as MONOTONIC sums that no
-// CTA ever waits for: a warp that finishes a chunk adds (T, 1) to a pair of counters with fire-and-forget
-// reductions (`red.global.add`: the CTA does not wait for an L2 round trip on its way out, which an atomic whose
-// result decides "am I the last CTA?" costs -- measured 1-3 us per launch on multi-wave grids).  A launch over C
-// chunks adds (T * C, C) in total, whatever its grid, so at the start of the next launch
-//     steps advanced  = sum(S) / C            chunk-counter base = sum(L)
-// (the chunk counter itself is monotonic too: a launch performs exactly C atomicAdds on it).  The pairs are spread
-// over CLOCK_GROUPS cache lines (chunk c uses line c % 32) because same-line traffic serialises in one L2 slice.
-//   clock[16 g], clock[16 g + 1]   g < 32: the (S, L) pair of group g
-//   clock[CLOCK_CHUNK]             chunk counter of the persistent grids (a line of its own)
-static const int CLOCK_GROUPS = 32, CLOCK_CHUNK = 16 * CLOCK_GROUPS, CLOCK_WORDS = CLOCK_CHUNK + 16;
-
-__device__ __forceinline__ void red_add_u64(unsigned long long* addr, unsigned long long v) {
-  asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(addr), "l"(v) : "memory");
-}
-// Warp-wide read of the clock: lane g reads pair g; returns (sum S, sum L) in every lane.
-__device__ __forceinline__ void clock_read_warp(const unsigned long long* clock, unsigned long long& sum_s, unsigned long long& sum_l) {
-  const int lane = threadIdx.x & 31;
-  unsigned long long s, l;                   // one 16-byte volatile load: both counters of the pair
-  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(s), "=l"(l) : "l"(clock + 16 * lane) : "memory");
-  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); l += __shfl_xor_sync(0xffffffffu, l, o); }
-  sum_s = s; sum_l = l;
-}
+// Graph-safe mode keeps the step count, the chunk counter and the finished-CTA count in device memory.  Every
+// word that many CTAs touch is spread over CLOCK_GROUPS 128-byte lines, because same-line traffic serialises in
+// one L2 slice (~2 ns per access): a 16 384-CTA launch reads the step count once per warp and counts itself out
+// once per CTA.
+//   clock[16 r]                 r < 32: the step count, REPLICATED (CTA b reads replica b % 32; the last CTA of
+//                               a launch rewrites all 32); the host reads / writes replica 0 .. 31
+//   clock[CLOCK_CHUNK]          chunk counter of the persistent grids (a line of its own)
+//   clock[CLOCK_TOP]            groups that have finished
+//   clock[CLOCK_SUB0 + 16 g]    CTAs of group g (= blockIdx % 32) that have finished
+static const int CLOCK_GROUPS = 32, CLOCK_CHUNK = 16 * CLOCK_GROUPS, CLOCK_TOP = CLOCK_CHUNK + 16,
+                 CLOCK_SUB0 = CLOCK_TOP + 16, CLOCK_WORDS = CLOCK_SUB0 + 16 * CLOCK_GROUPS;
 
 template <class F, int RK, bool kNoise, bool kTrack>
 __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kernel(const EnvParams p, const LaunchArgs a) {
@@ -564,19 +553,7 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
   // to become resident: its CTAs park at their own wait, so at most one dependent grid is ever pending.
   if (a.use_pdl) { pdl_wait(); pdl_launch_dependents(); }
   int64_t step0 = a.step0;
-  unsigned long long work_base = a.work_base;
-  if (a.clock) {
-    __shared__ unsigned long long clock_now[2];
-    if (warp == 0) {
-      unsigned long long sum_s, sum_l;
-      clock_read_warp(a.clock, sum_s, sum_l);
-      if (tid == 0) { clock_now[0] = sum_s; clock_now[1] = sum_l; }
-    }
-    __syncthreads();
-    const int64_t chunks_per_launch = (p.batch + a.chunk_lanes - 1) / a.chunk_lanes;
-    step0 += (int64_t)clock_now[0] / chunks_per_launch;       // signed: bsb_set_state may have written a negative offset
-    work_base = clock_now[1];
-  }
+  if (a.clock) step0 += (int64_t)*reinterpret_cast<volatile unsigned long long*>(a.clock + 16 * (blockIdx.x % CLOCK_GROUPS));
 
   // Caller-owned buffers: launch arguments, or -- doorbell mode -- whatever the host wrote into the mailbox
   // before it rang this launch's ticket.
@@ -634,7 +611,7 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
   const int64_t total_warps = (int64_t)worker_blocks * warps_per_cta;
   auto fetch_chunk = [&]() -> int64_t {
     unsigned long long v = 0;
-    if (tid == 0) v = atomicAdd(a.work_counter, 1ull) - work_base;        // graph-safe mode: base read from the clock
+    if (tid == 0) v = atomicAdd(a.work_counter, 1ull) - a.work_base;      // graph-safe mode: clock + 1, base 0
     return total_warps + (int64_t)__shfl_sync(0xffffffffu, v, 0);
   };
   int64_t cur_chunk = (int64_t)worker_block * warps_per_cta + warp;
@@ -999,11 +976,6 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
       if (kNoise) rng_close(wrng, p, lane, true);
       if (kTrack) ep.store(p, lane);
     }
-    if (a.clock && tid == 0) {                             // this chunk's share of the device clock (no result wanted)
-      unsigned long long* pair = a.clock + 16 * (int)((warp_base / cl) % CLOCK_GROUPS);
-      red_add_u64(pair, a.mode == MODE_INIT ? 0ull : (unsigned long long)a.T);
-      red_add_u64(pair + 1, 1ull);
-    }
     if (dynamic && lazy) cur_chunk = fetch_chunk();        // lazy: nothing was reserved while working
   }
   if (any_bulk && tid == 0) {
@@ -1020,6 +992,27 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
         a.mail->finished = 0ull;
         __threadfence_system();
         st_sys_u64(&a.mailbox->done, a.ticket | (cancelled ? MAIL_CANCEL : 0ull));
+      }
+    }
+  }
+  if (a.clock) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned groups = gridDim.x < (unsigned)CLOCK_GROUPS ? gridDim.x : (unsigned)CLOCK_GROUPS;
+      const unsigned g = blockIdx.x % groups;
+      const unsigned members = gridDim.x / groups + (g < gridDim.x % groups ? 1u : 0u);
+      unsigned long long* sub = a.clock + CLOCK_SUB0 + 16 * g;
+      // No fence: the count only says "this CTA has READ the step count and drawn its chunks" -- both happened
+      // (their values were consumed) long before; the state it wrote reaches the next launch through the kernel
+      // boundary.  A membar here kept every CTA alive ~1 us longer: +2..7 us per launch on multi-wave grids.
+      if (atomicAdd(sub, 1ull) == (unsigned long long)members - 1ull) {
+        *sub = 0ull;                          // re-armed for the next launch (which starts after this one ends)
+        if (atomicAdd(a.clock + CLOCK_TOP, 1ull) == (unsigned long long)groups - 1ull) {
+          const unsigned long long steps = (unsigned long long)(step0 - a.step0) + (a.mode == MODE_INIT ? 0ull : (unsigned long long)a.T);
+          for (int r = 0; r < CLOCK_GROUPS; ++r) a.clock[16 * r] = steps;
+          a.clock[CLOCK_CHUNK] = 0ull;
+          a.clock[CLOCK_TOP] = 0ull;
+        }
       }
     }
   }
