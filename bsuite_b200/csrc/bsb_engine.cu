@@ -221,7 +221,12 @@ int mailbox_open(bsb_env* e) {
 
 // Enqueues one single-step launch that signals `ticket` through the mailbox.  wait_doorbell: the launch takes its
 // buffers from the mailbox once the host rings `ticket` (pre-launch); otherwise from `fields` right away.
-bool family_obs_from_state(const bsb_env* e) { return e->p.family == BSB_DEEP_SEA || e->p.family == BSB_CATCH; }
+// Two-phase host steps pay off where the observation stream is long next to the scalar traffic over PCIe (12 B per
+// lane out, 4 B in): deep_sea from N = 16 up (>= 1 KB of observation per lane).  catch (200 B per lane) is bound
+// by the 2 MB of scalars per step either way and keeps the single-phase kernel (measured: 86 vs 51 us per step).
+bool family_obs_from_state(const bsb_env* e) {
+  return (e->p.family == BSB_DEEP_SEA || e->p.family == BSB_CATCH) && (size_t)e->p.obs_numel * sizeof(float) >= 1024;
+}
 
 int mailbox_launch(bsb_env* e, unsigned long long ticket, int64_t step0, const MailFields* fields, bool wait_doorbell) {
   LaunchArgs a;
