@@ -68,3 +68,73 @@ def run(agent, environment, num_steps: int) -> None:
     new_timestep = environment.step(actions)
     agent.update(timestep, actions, new_timestep)
     timestep = new_timestep
+
+
+class Replay:
+  """Uniform replay of flat item tuples as device tensors (`bsuite/baselines/utils/replay.py:24-88`): a ring of
+  `capacity` slots per item, `add(items)` writes one tuple, `sample(size)` returns a list of `[size, ...]` tensors
+  drawn uniformly with replacement, `size` / `fraction_filled` as in the reference.  `add_batch` writes many tuples
+  at once (leading axis = tuple index) and `add_transitions` feeds it a whole `Trajectory`: the reference's DQN
+  stores `(o_tm1, a_tm1, r_t, d_t, o_t)` per environment step (baselines/dqn/agent.py); here that is B x T tuples
+  per fused rollout, minus the calls on which a lane merely restarted (step_type FIRST: no transition happened)."""
+
+  def __init__(self, capacity: int, device='cuda', seed: Optional[int] = None):
+    import torch
+    self._torch = torch
+    self._capacity, self._device = int(capacity), torch.device(device)
+    self._data, self._num_added = None, 0
+    self._generator = torch.Generator(device=self._device)
+    if seed is not None:
+      self._generator.manual_seed(int(seed))
+
+  def _preallocate(self, items):
+    torch = self._torch
+    self._data = [torch.zeros((self._capacity,) + tuple(item.shape[1:]), dtype=item.dtype, device=self._device)
+                  for item in items]
+
+  def add(self, items) -> None:
+    """Adds a single tuple of items (tensors or scalars, not batched)."""
+    torch = self._torch
+    self.add_batch([torch.as_tensor(item, device=self._device).unsqueeze(0) for item in items])
+
+  def add_batch(self, items) -> None:
+    """Adds `n` tuples at once: every item has a leading axis of length n; the oldest slots are overwritten."""
+    torch = self._torch
+    items = [torch.as_tensor(item, device=self._device) for item in items]
+    n = int(items[0].shape[0])
+    if n == 0:
+      return
+    if self._data is None:
+      self._preallocate(items)
+    if n > self._capacity:                         # only the newest `capacity` tuples can survive
+      items = [item[n - self._capacity:] for item in items]
+      self._num_added += n - self._capacity
+      n = self._capacity
+    slots = (torch.arange(n, device=self._device) + self._num_added) % self._capacity
+    for slot, item in zip(self._data, items):
+      slot[slots] = item.to(slot.dtype)
+    self._num_added += n
+
+  def add_transitions(self, trajectory: Trajectory) -> int:
+    """Adds every real transition of a `Trajectory` as `(o_tm1, a_tm1, r_t, d_t, o_t)`; returns how many."""
+    keep = (trajectory.step_types != 0).reshape(-1)
+    flat = lambda x: x.reshape((-1,) + tuple(x.shape[2:]))[keep]
+    o_tm1, o_t = trajectory.observations[:-1], trajectory.observations[1:]
+    self.add_batch([flat(o_tm1), flat(trajectory.actions), flat(trajectory.rewards), flat(trajectory.discounts), flat(o_t)])
+    return int(keep.sum())
+
+  def sample(self, size: int):
+    """A list of `[size, ...]` tensors, one per item, drawn uniformly with replacement from the filled slots."""
+    indices = self._torch.randint(0, self.size, (int(size),), device=self._device, generator=self._generator)
+    return [slot[indices] for slot in self._data]
+
+  def reset(self) -> None:
+    self._data, self._num_added = None, 0
+
+  @property
+  def size(self) -> int:
+    return min(self._capacity, self._num_added)
+
+  @property
+  def fraction_filled(self) -> float:
+    return self.size / self._capacity

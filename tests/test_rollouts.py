@@ -51,3 +51,33 @@ def test_reference_experiment_loop_runs_unmodified_on_the_adapter():
   experiment.run(random_agent.Random(ours.action_spec(), seed=2), ours, num_episodes=40)
   experiment.run(random_agent.Random(theirs.action_spec(), seed=2), theirs, num_episodes=40)
   assert ours.bsuite_info() == theirs.bsuite_info()
+
+
+def test_replay_ring_matches_the_reference_semantics():
+  """rollouts.Replay against bsuite/baselines/utils/replay.py: ring overwrite, size, fraction_filled, sample shapes;
+  and Trajectory -> (o_tm1, a_tm1, r_t, d_t, o_t) tuples without the restart calls."""
+  import numpy as np
+  import torch
+  import bsuite_b200
+  from bsuite_b200 import rollouts
+  replay = rollouts.Replay(capacity=5, device='cpu', seed=0)
+  for i in range(7):
+    replay.add([np.full((2, 2), i, np.float32), i, float(i) / 2])
+  assert replay.size == 5 and replay.fraction_filled == 1.0
+  obs, ints, floats = replay.sample(64)
+  assert obs.shape == (64, 2, 2) and set(ints.tolist()) <= {2, 3, 4, 5, 6} and torch.equal(obs[:, 0, 0].long(), ints)
+  assert torch.allclose(floats.double(), ints.double() / 2)
+  replay.reset()
+  assert replay.size == 0
+  env = bsuite_b200.load_from_id('catch/0', batch=6, device='cpu', seed=1)
+  traj = rollouts.collect(env, 25)
+  big = rollouts.Replay(capacity=1000, device='cpu')
+  added = big.add_transitions(traj)
+  assert added == int((traj.step_types != 0).sum()) == big.size
+  o_tm1, a, r, d, o_t = big.sample(200)
+  assert o_tm1.shape == o_t.shape == (200, 10, 5) and a.shape == r.shape == d.shape == (200,)
+  assert float(o_tm1.sum(dim=(1, 2)).min()) >= 1.0          # a transition starts from a real board, never from a LAST frame's successor
+  # the tuples are the trajectory's own: every sampled (o_tm1, o_t) pair is adjacent in some lane
+  pairs = {(traj.observations[t, b].numpy().tobytes(), traj.observations[t + 1, b].numpy().tobytes())
+           for t in range(25) for b in range(6) if int(traj.step_types[t, b]) != 0}
+  assert all((x.numpy().tobytes(), y.numpy().tobytes()) in pairs for x, y in zip(o_tm1[:50], o_t[:50]))
