@@ -310,11 +310,12 @@ int32_t bsb_set_state(bsb_env* env, const void* src_host, int64_t nbytes,
  *       bsb_reset / bsb_step / bsb_rollout on `caller_stream` is waited for (on
  *       the device) before the step runs.  Without the flag the caller must
  *       have synchronised that stream: the step runs on a stream the handle owns.
- *   BSB_HOST_FENCE_CALLER  deep_sea and catch (whose observation is a function
- *       of the lane state) run host steps in two phases: the transitions of all
- *       lanes first, then the observation stream.  The call returns as soon as
- *       the scalars have landed -- the agent decides its next action while the
- *       observations are still being written.  With this flag `caller_stream`
+ *   BSB_HOST_FENCE_CALLER  deep_sea from size 16 up (its observation is a function
+ *       of the lane state and dwarfs the scalar traffic) runs host steps in two
+ *       phases: the transitions of all lanes first (scalars staged on the device
+ *       and shipped to the host by a few copier blocks), then the observation
+ *       stream.  The call returns as soon as the scalars have landed -- the agent
+ *       decides its next action while the observations are still being written.  With this flag `caller_stream`
  *       is fenced (on the device) behind the step, so work enqueued there
  *       afterwards sees complete observations; without it, order a consumer by
  *       the next call on this handle (every entry point waits for the step) or
