@@ -494,7 +494,7 @@ def engine_main(args):
   value = world * B * K / (total_ms * 1e-3)
 
   # ---- e2e: host actions in, scalars out, every step ---------------------------
-  Ke = max(10, min(K, 200))
+  Ke = max(100, min(K, 200))     # steps per e2e window: short windows time the cold first calls, not the loop
   host_actions = torch.randint(0, 2, (Ke, B), dtype=torch.int32).pin_memory()
   host_small = env.make_host_buffers(with_observation=False)
 
@@ -506,7 +506,7 @@ def engine_main(args):
     env.host_flush()
 
   def timed_e2e(n, host, reps, prelaunch=False):
-    e2e_loop(3, host, prelaunch)
+    e2e_loop(min(n, 10), host, prelaunch)
     secs = []
     for _ in range(reps):
       if world > 1:
