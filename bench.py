@@ -282,7 +282,7 @@ def family_leg(name, ids, lanes, rank, world, device, torch, dist, peak_gbs, rol
         if gather:
           batch.issue_log_point()          # reduction kernels in order; the all-gather rides a side stream
       if gather:
-        batch._log_point().join()          # pylint: disable=protected-access
+        batch.join_log_points()
       e1.record()
       torch.cuda.synchronize()
       times.append(e0.elapsed_time(e1))
@@ -319,7 +319,7 @@ def family_leg(name, ids, lanes, rank, world, device, torch, dist, peak_gbs, rol
         if gather:
           batch.issue_log_point()
       if gather:
-        batch._log_point().join()          # pylint: disable=protected-access
+        batch.join_log_points()
       e1.record()
       torch.cuda.synchronize()
       times.append(e0.elapsed_time(e1))

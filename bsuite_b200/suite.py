@@ -149,6 +149,11 @@ class SweepBatch:
     """float64 [world, n_ids, 3]: per-rank, per-id sums of (total_return, episode, steps) of `ticket`."""
     return self._log_point().result(ticket, host_sync=host_sync).index_select(-1, self._cols)
 
+  def join_log_points(self):
+    """Makes the caller's stream wait (on the device) for every log point still in flight."""
+    if self._lp is not None:
+      self._lp.join()
+
   def local_returns(self):
     """float64 [n_ids, 3] on the device: per-id sums of (total_return, episode, steps) over this rank's lanes."""
     torch = self._torch
