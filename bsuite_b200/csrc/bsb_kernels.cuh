@@ -22,11 +22,14 @@
 //     ~4.6 TB/s while 32 KB stores reach the HBM write ceiling.  Unaligned tiles (odd N) use 16-byte streaming
 //     stores instead: the warp walks its lanes, every thread writes part of each lane's tile, the hot cell
 //     chosen per float4 from a descriptor broadcast by __shfl_sync.
-//   * mnist: gathered int8 image -> float32 tile, 16-byte stores.
+//   * mnist: groups of 4 gathered int8 images -> float32 tiles in shared memory -> one bulk store; the all-zero
+//     LAST frames of a group leave as one bulk store from zero tiles the CTA's warps share.
 //
 // A launch covers T consecutive steps with lane state held in registers (T = 1
 // for bsb_step); actions come from the caller or from the on-device Philox
-// action stream.  With use_pdl the kernel is launched with programmatic stream
+// action stream.  Host-driven steps (bsb_step_host) signal completion through a
+// pinned mailbox and, for deep_sea, run in two phases (all transitions first, the
+// scalars shipped to the host by a few copier blocks, then the observations).  With use_pdl the kernel is launched with programmatic stream
 // serialization: everything before griddepcontrol.wait (index math, zeroing the
 // shared-memory stages) overlaps the tail of the previous step's kernel.
 #pragma once
