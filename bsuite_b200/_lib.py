@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # BSB_LIBRARY points the binding at another build of the SAME library (tools/host_sanitize.sh: ASan/UBSan build)
 LIB_PATH = os.environ.get('BSB_LIBRARY') or os.path.join(_HERE, 'libbsuite_b200.so')
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 DEVICE_HOST = -1
 MAX_INFO = 4
 COMM_ID_BYTES = 128
@@ -28,7 +28,7 @@ WRAP_NONE, WRAP_REWARD_NOISE, WRAP_REWARD_SCALE = range(3)
 # enum bsb_rng_kind
 RNG_PHILOX, RNG_MT19937 = range(2)
 FLAG_TRACK_EPISODES = 1
-HOST_ORDER_AFTER_STREAM, HOST_PRELAUNCH, HOST_FENCE_CALLER = 1, 2, 4      # bsb_step_host flags
+HOST_ORDER_AFTER_STREAM, HOST_PRELAUNCH, HOST_FENCE_CALLER, HOST_NO_WAIT = 1, 2, 4, 8      # bsb_step_host flags
 EPISODE_STAT_FIELDS = ('steps', 'episode', 'total_return', 'episode_len', 'episode_return')
 
 
@@ -93,6 +93,7 @@ EXPORTS = {
     'bsb_step_host': (ctypes.c_int32, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(Outputs), ctypes.c_void_p,
                                        ctypes.c_void_p, ctypes.c_uint32]),
     'bsb_host_flush': (ctypes.c_int32, [ctypes.c_void_p]),
+    'bsb_host_wait': (ctypes.c_int32, [ctypes.c_void_p]),
     'bsb_host_timing': (ctypes.c_int32, [ctypes.c_void_p, ctypes.c_void_p]),
     'bsb_invalid_actions': (ctypes.c_int32, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32)]),
     'bsb_comm_unique_id': (ctypes.c_int32, [ctypes.c_void_p]),

@@ -274,9 +274,23 @@ int mailbox_wait(bsb_env* e, unsigned long long ticket, bool* cancelled) {
   return BSB_OK;
 }
 
-// Stands down the pre-launched launch, if any: rings its ticket with the cancel bit and waits for it to leave.
+// Collects a step issued with BSB_HOST_NO_WAIT: spins until its completion word is in and counts the step.
+int finish_awaited(bsb_env* e) {
+  if (!e || e->device < 0 || !e->awaiting_ticket) return BSB_OK;
+  const unsigned long long ticket = e->awaiting_ticket;
+  e->awaiting_ticket = 0;
+  bool cancelled = false;
+  int rc = mailbox_wait(e, ticket, &cancelled);
+  if (rc != BSB_OK) return rc;
+  e->steps_done += 1;
+  return BSB_OK;
+}
+
+// Stands down the pre-launched launch, if any: rings its ticket with the cancel bit and waits for it to leave
+// (and collects a BSB_HOST_NO_WAIT step nobody waited for).
 // Every entry point that enqueues work for this handle or reads its state calls this first.
 int flush_pending(bsb_env* e) {
+  { int arc = finish_awaited(e); if (arc != BSB_OK) return arc; }
   if (!e || e->device < 0 || !e->pending_ticket) return BSB_OK;
   DeviceGuard guard(e->device);
   const unsigned long long ticket = e->pending_ticket;
@@ -467,7 +481,7 @@ int32_t bsb_create(const bsb_config* config, int64_t batch, int32_t device, uint
     if (device >= 0) { int n = 0; if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && n > 0) e->num_sms = n; }
   }
   e->order_event = nullptr; e->fence_event = nullptr; e->bad_action_host = nullptr; e->bad_action_dev = nullptr;
-  e->mailbox = nullptr; e->mailbox_dev = nullptr; e->mail = nullptr; e->next_ticket = 0; e->pending_ticket = 0;
+  e->mailbox = nullptr; e->mailbox_dev = nullptr; e->mail = nullptr; e->next_ticket = 0; e->pending_ticket = 0; e->awaiting_ticket = 0;
   { const char* v = getenv("BSB_DOORBELL_TIMEOUT_MS"); const long ms = v ? atol(v) : 200; e->doorbell_timeout_ns = (unsigned long long)(ms > 0 ? ms : 200) * 1000000ull; }
   { const char* v = getenv("BSB_HOST_SPIN"); e->host_spin = v ? (atoi(v) != 0) : 1; }
   { const char* v = getenv("BSB_HOST_EARLY"); e->host_early = v ? (atoi(v) != 0) : 1; }
@@ -621,7 +635,9 @@ static void advance_steps(bsb_env* env, int64_t n) { if (!env->graph_safe) env->
 
 int32_t bsb_steps_done(const bsb_env* env, int64_t* steps) {
   if (!env || !steps) return fail(BSB_INVALID_ARGUMENT, "null argument");
-  return current_steps(env, steps);       // a pre-launched host step (if any) has not been counted: it is for step steps_done
+  int rc = current_steps(env, steps);     // a pre-launched host step (if any) has not been counted: it is for step steps_done
+  if (rc == BSB_OK && env->awaiting_ticket) *steps += 1;      // a BSB_HOST_NO_WAIT step has been issued: it counts
+  return rc;
 }
 
 int32_t bsb_reset(bsb_env* env, const bsb_outputs* out, void* stream) {
@@ -876,7 +892,9 @@ int32_t bsb_step_host(bsb_env* env, const int32_t* actions, const bsb_outputs* h
     return bsb_step(env, actions, host_out, nullptr);
   }
   if (!host_out->observation && !device_obs) return fail(BSB_INVALID_ARGUMENT, "need host_out->observation or device_obs");
+  if ((flags & BSB_HOST_NO_WAIT) && (flags & BSB_HOST_PRELAUNCH)) return fail(BSB_INVALID_ARGUMENT, "BSB_HOST_NO_WAIT and BSB_HOST_PRELAUNCH exclude each other");
   DeviceGuard guard(env->device);
+  { int arc = finish_awaited(env); if (arc != BSB_OK) return arc; }      // one step in flight per handle
   const size_t B = (size_t)env->p.batch, K = (size_t)env->p.obs_numel;
   if (!env->copy_stream) BSB_CUDA(cudaStreamCreateWithFlags(&env->copy_stream, cudaStreamNonBlocking));
   if (flags & BSB_HOST_ORDER_AFTER_STREAM) {
@@ -975,6 +993,12 @@ int32_t bsb_step_host(bsb_env* env, const int32_t* actions, const bsb_outputs* h
           BSB_CUDA(cudaEventRecord(env->fence_event, zs));
           BSB_CUDA(cudaStreamWaitEvent(static_cast<cudaStream_t>(caller_stream), env->fence_event, 0));
         }
+        if (flags & BSB_HOST_NO_WAIT) {
+          // Split call: the completion word is collected by bsb_host_wait (or by whichever entry point of this handle
+          // runs next), so the caller can drive ANOTHER handle while this step's scalars cross PCIe.
+          env->awaiting_ticket = ticket;
+          return BSB_OK;
+        }
         if (prelaunch) {
           // Queue the NEXT step's kernel now: it becomes resident as this one drains and waits for its doorbell,
           // so the next call pays neither a launch nor a wake-up.  It stands down by itself after
@@ -1030,6 +1054,15 @@ int32_t bsb_step_host(bsb_env* env, const int32_t* actions, const bsb_outputs* h
   if (host_out->observation) BSB_CUDA(cudaMemcpyAsync(host_out->observation, dev.observation, B * K * 4, cudaMemcpyDeviceToHost, s));
   BSB_CUDA(cudaStreamSynchronize(s));
   return BSB_OK;
+}
+
+
+int32_t bsb_host_wait(bsb_env* env) {
+  if (!env) return fail(BSB_INVALID_ARGUMENT, "null argument");
+  if (env->device < 0 || !env->awaiting_ticket) return BSB_OK;
+  DeviceGuard guard(env->device);
+  { int rc = finish_awaited(env); if (rc != BSB_OK) return rc; }
+  return report_bad_actions(env);
 }
 
 }  // extern "C"

@@ -70,6 +70,7 @@ struct bsb_env {
   // and waits for the mailbox doorbell (bsb_kernels.cuh, HostMailbox).
   bsb::HostMailbox* mailbox; bsb::HostMailbox* mailbox_dev; bsb::DeviceMail* mail;
   unsigned long long next_ticket;     // last ticket handed out
+  unsigned long long awaiting_ticket; // a BSB_HOST_NO_WAIT step whose completion word has not been collected yet (0 = none)
   unsigned long long pending_ticket;  // pre-launched launch waiting for its doorbell (0 = none); it is for step steps_done
   unsigned long long doorbell_timeout_ns;
   int host_spin;                      // BSB_HOST_SPIN (default 1): completion through the mailbox instead of a synchronise

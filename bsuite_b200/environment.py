@@ -313,7 +313,8 @@ class BatchedEnvironment:
                    if with_observation else None)
     return StepBuffers(observation=observation, reward=reward, discount=discount, step_type=step_type)
 
-  def step_host(self, actions, host: StepBuffers, out: Optional[StepBuffers] = None, prelaunch: bool = False):
+  def step_host(self, actions, host: StepBuffers, out: Optional[StepBuffers] = None, prelaunch: bool = False,
+                wait: bool = True):
     """One step driven from HOST memory through `bsb_step_host`: the reference's call pattern, one
     `env.step(action)` per decision (baselines/experiment.py:45-57), for agents whose policy runs on the host.
 
@@ -330,6 +331,9 @@ class BatchedEnvironment:
     method's next call on a doorbell in pinned memory, so a call costs neither a kernel launch nor a stream
     synchronise.  The waiting kernel occupies the GPU: use it for host-side policies in a tight loop; any other
     method of this environment (or 200 ms without a call) stands it down.
+
+    `wait=False` (pinned buffers, CUDA): returns once the step is enqueued; `host` holds the results after
+    `host_wait()`.  `rollouts.HostHalves` uses it to drive two half-batches alternately (`BSB_HOST_NO_WAIT`).
     """
     torch = self._torch
     if not (type(actions) is torch.Tensor and actions.dtype is torch.int32 and actions.device.type == 'cpu'
@@ -346,7 +350,7 @@ class BatchedEnvironment:
     if self._ordinal < 0:        # host environment: one memory space; `out.observation` is the observation
       houts = _lib.Outputs.from_buffer_copy(houts)
       houts.observation = out.observation.data_ptr()
-    flags = _lib.HOST_PRELAUNCH if prelaunch else 0
+    flags = (_lib.HOST_PRELAUNCH if prelaunch else 0) | (0 if wait else _lib.HOST_NO_WAIT)
     stream = None
     if self._ordinal >= 0:
       # fence torch's current stream behind the step: deep_sea / catch return as soon as the scalars have landed
@@ -362,6 +366,12 @@ class BatchedEnvironment:
     if self._ordinal < 0 and host.observation is not None:
       host.observation.copy_(out.observation)
     return host.timestep(), out.observation
+
+  def host_wait(self):
+    """Completes a `step_host(..., wait=False)`: returns when its host outputs have landed (no-op otherwise)."""
+    status = self._lib.bsb_host_wait(self._handle.ptr)
+    if status:
+      _lib.check(status)
 
   def host_flush(self):
     """Stands down a kernel queued by `step_host(..., prelaunch=True)` (every other method does so implicitly)."""

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define BSB_ABI_VERSION 5
+#define BSB_ABI_VERSION 6
 #define BSB_DEVICE_HOST (-1)
 #define BSB_MAX_INFO 4
 
@@ -328,16 +328,32 @@ int32_t bsb_set_state(bsb_env* env, const void* src_host, int64_t nbytes,
  *       until the next call, bsb_host_flush, or BSB_DOORBELL_TIMEOUT_MS (default
  *       200) without a ring, after which it stands down by itself.  Every other
  *       entry point of this handle stands it down first.
+ *   BSB_HOST_NO_WAIT  (pinned buffers; otherwise the call is simply synchronous)
+ *       the call returns once the step is enqueued; the host outputs are valid
+ *       after bsb_host_wait(env).  One step per handle may be outstanding (any
+ *       entry point of the handle collects it first).  The use: split the lanes
+ *       over TWO handles (bsb_create's lane_offset keeps the lanes' random streams
+ *       those of one big batch) and alternate -- while one half's scalars cross
+ *       PCIe and its agent decides, the other half's kernel has the GPU, so each
+ *       half remains the reference's strict loop (act on what the previous step
+ *       returned) and the GPU is not left idle in between.  Not with
+ *       BSB_HOST_PRELAUNCH.
  */
 #define BSB_HOST_ORDER_AFTER_STREAM 1u
 #define BSB_HOST_PRELAUNCH 2u
 #define BSB_HOST_FENCE_CALLER 4u
+#define BSB_HOST_NO_WAIT 8u
 int32_t bsb_step_host(bsb_env* env, const int32_t* actions,
                       const bsb_outputs* host_out, float* device_obs,
                       void* caller_stream, uint32_t flags);
 
 /* Stands down a launch queued by BSB_HOST_PRELAUNCH (no-op otherwise). */
 int32_t bsb_host_flush(bsb_env* env);
+
+/* Completes a step issued with BSB_HOST_NO_WAIT: returns when its host outputs
+ * have landed (no-op when nothing is outstanding).  Reports an out-of-range
+ * action of that step as BSB_INVALID_ARGUMENT, like the synchronous call. */
+int32_t bsb_host_wait(bsb_env* env);
 
 /* Diagnostics (BSB_HOST_TIMING=1): %globaltimer stamps, in ns, the latest two-phase
  * host step left in the mailbox: [0] kernel past its dependency wait, [1] phase 1

@@ -257,3 +257,81 @@ def test_two_phase_host_steps_with_ragged_batches_and_float64_rewards(bsuite_id,
       np.testing.assert_array_equal(_np(getattr(got, field)), _np(getattr(want, field)), err_msg=f'{field} t={t}')
     assert torch.equal(obs, want.observation), t
   np.testing.assert_array_equal(a.state_dict()['blob'], b.state_dict()['blob'])
+
+
+# ---------------------------------------------------------------------------- split host steps (BSB_HOST_NO_WAIT)
+@pytest.mark.gpu
+@pytest.mark.parametrize('bsuite_id,batch', [('deep_sea/11', 8192 + 37), ('deep_sea_stochastic/3', 300), ('catch/0', 1000),
+                                             ('cartpole/0', 777), ('bandit_noise/0', 2)])
+def test_two_halves_driven_alternately_are_one_batch(bsuite_id, batch):
+  """rollouts.HostHalves: two handles, one step in flight on each, collected alternately -- every lane's trajectory is
+  the one it has in a single `batch`-lane environment (lane keys continue across the split)."""
+  from bsuite_b200 import rollouts
+  T = 30
+  halves = rollouts.HostHalves(bsuite_id, batch, device='cuda', seed=5, track_episodes=True)
+  whole = bsuite_b200.load_from_id(bsuite_id, batch=batch, device='cuda', seed=5, track_episodes=True)
+  assert sum(halves.sizes) == batch and halves.envs[1].lane_offset == halves.sizes[0]
+  split = halves.sizes[0]
+  actions = torch.as_tensor(np.random.RandomState(2).randint(whole.num_actions, size=(T, batch)).astype(np.int32))
+  pinned = [actions[:, :split].contiguous().pin_memory(), actions[:, split:].contiguous().pin_memory()]
+  halves.reset(); whole.reset()
+  want = [whole.step(actions[t].cuda(), out=whole.make_buffers()) for t in range(T)]
+  torch.cuda.synchronize()
+  tol = cf.FLOAT_TOL if bsuite_id.startswith('cartpole') else 0
+
+  def check(half, t, ts, obs):
+    lanes = slice(0, split) if half == 0 else slice(split, batch)
+    for field in ('step_type', 'reward', 'discount'):
+      np.testing.assert_allclose(_np(getattr(ts, field)), _np(getattr(want[t], field))[lanes], rtol=0, atol=tol,
+                                 err_msg=f'{field} half={half} t={t}')
+    torch.cuda.synchronize()
+    assert torch.equal(obs, want[t].observation[lanes]), (half, t)
+
+  for half in (0, 1):
+    halves.submit(half, pinned[half][0])
+  with pytest.raises(RuntimeError):
+    halves.submit(0, pinned[0][1])             # one step in flight per half
+  assert halves.envs[0].steps_done == 2        # reset + the step in flight
+  for t in range(1, T):
+    for half in (0, 1):
+      check(half, t - 1, *halves.collect(half))
+      halves.submit(half, pinned[half][t])
+  for half in (0, 1):
+    check(half, T - 1, *halves.collect(half))
+  sums = halves.envs[0].episode_stat_sums() + halves.envs[1].episode_stat_sums()
+  np.testing.assert_allclose(_np(sums), _np(whole.episode_stat_sums()), rtol=1e-12)
+  # the same through run(): the policy sees each half's latest timestep
+  seen = []
+  last = halves.run(lambda half, step, ts: (seen.append((half, step, ts is not None)), pinned[half][step % T])[1], 5)
+  assert seen[:2] == [(0, 0, False), (1, 0, False)] and seen[2:4] == [(0, 1, True), (1, 1, True)] and len(seen) == 10
+  assert all(e.steps_done == T + 1 + 5 for e in halves.envs) and last[0].reward.shape[0] == split
+  halves.close(); whole.close()
+
+
+@pytest.mark.gpu
+def test_a_step_in_flight_is_collected_by_whatever_runs_next_and_reports_bad_actions():
+  env = bsuite_b200.load_from_id('deep_sea/11', batch=4096, device='cuda', seed=1, track_episodes=True)
+  twin = bsuite_b200.load_from_id('deep_sea/11', batch=4096, device='cuda', seed=1, track_episodes=True)
+  host = env.make_host_buffers()
+  actions = torch.as_tensor(np.random.RandomState(0).randint(2, size=(4, 4096)).astype(np.int32)).pin_memory()
+  env.host_wait()                                               # nothing outstanding: no-op
+  for t in range(3):
+    env.step_host(actions[t], host, wait=False)                 # never waited for: the next call collects it
+    twin.step(actions[t].cuda())
+  got = env.step(actions[3].cuda()); want = twin.step(actions[3].cuda())
+  assert torch.equal(got.observation, want.observation) and env.steps_done == twin.steps_done == 4
+  bad = actions[0].clone().pin_memory(); bad[7] = 5
+  env.step_host(bad, host, wait=False)
+  with pytest.raises(_lib.EngineError, match='outside'):
+    env.host_wait()
+  env.host_wait()                                               # reported once
+  status = env._lib.bsb_step_host(env._handle.ptr, actions[0].data_ptr(), host.as_outputs(), env.make_buffers().observation.data_ptr(),
+                                  None, _lib.HOST_NO_WAIT | _lib.HOST_PRELAUNCH)
+  assert status != 0
+  env.close(); twin.close()
+
+
+def test_host_halves_refuses_host_environments():
+  from bsuite_b200 import rollouts
+  with pytest.raises(ValueError):
+    rollouts.HostHalves('catch/0', 64, device='cpu')
