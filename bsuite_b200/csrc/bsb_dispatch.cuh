@@ -156,6 +156,11 @@ int device_launch(bsb_env* e, LaunchArgs a, cudaStream_t stream) {
     }
   }
   a.use_pdl = (e->use_pdl && !a.no_pdl && a.mode == MODE_STEP && a.T == 1) ? 1 : 0;
+  if (a.phase == 1) {
+    // transitions-only launch of a split host step: no emitter, no shared memory (so that it is co-resident with the
+    // observation stream of ANOTHER handle), one chunk per warp
+    a.emit_bulk = 0; a.stage_rows = 0; a.cta_extra_floats = 0; a.group_lanes = 1; threads = 128; persistent = false;
+  }
   size_t per_warp = smem_floats_per_warp<F>(K, a.emit_bulk != 0, a.group_lanes, a.stage_rows) * sizeof(float);
   if ((EmitKind<F>::value == EMIT_ROWS || EmitKind<F>::value == EMIT_TWOHOT) && per_warp > 96 * 1024) {
     // rows / boards too long for a per-warp stage (catch boards beyond ~19 x 20 cells, umbrella_chain with more than

@@ -228,7 +228,7 @@ bool family_obs_from_state(const bsb_env* e) {
   return (e->p.family == BSB_DEEP_SEA || e->p.family == BSB_CATCH) && (size_t)e->p.obs_numel * sizeof(float) >= 1024;
 }
 
-int mailbox_launch(bsb_env* e, unsigned long long ticket, int64_t step0, const MailFields* fields, bool wait_doorbell) {
+int mailbox_launch(bsb_env* e, unsigned long long ticket, int64_t step0, const MailFields* fields, bool wait_doorbell, bool split = false) {
   LaunchArgs a;
   memset(&a, 0, sizeof(a));
   if (fields) {
@@ -251,6 +251,16 @@ int mailbox_launch(bsb_env* e, unsigned long long ticket, int64_t step0, const M
     if (!e->d_reward64) BSB_CUDA(cudaMalloc(&e->d_reward64, B * 8));
     a.stage.reward = e->d_reward; a.stage.reward_f64 = e->d_reward64; a.stage.discount = e->d_discount; a.stage.step_type = e->d_step_type;
     e->early_inflight = true;
+    if (split && e->host_split && !wait_doorbell) {
+      // BSB_HOST_NO_WAIT: the caller alternates between handles.  Two launches instead of one -- transitions + copiers
+      // (no shared memory), then the observation stream -- so that THIS handle's transitions and PCIe traffic run
+      // while the OTHER handle's observations have the SMs' shared memory and the HBM.
+      LaunchArgs first = a, second = a;
+      first.phase = 1;
+      second.phase = 2; second.mailbox = nullptr; second.early_scalars = 0;
+      int rc = run(e, first, e->copy_stream);
+      return rc != BSB_OK ? rc : run(e, second, e->copy_stream);
+    }
   }
   return run(e, a, e->copy_stream);
 }
@@ -485,6 +495,7 @@ int32_t bsb_create(const bsb_config* config, int64_t batch, int32_t device, uint
   { const char* v = getenv("BSB_DOORBELL_TIMEOUT_MS"); const long ms = v ? atol(v) : 200; e->doorbell_timeout_ns = (unsigned long long)(ms > 0 ? ms : 200) * 1000000ull; }
   { const char* v = getenv("BSB_HOST_SPIN"); e->host_spin = v ? (atoi(v) != 0) : 1; }
   { const char* v = getenv("BSB_HOST_EARLY"); e->host_early = v ? (atoi(v) != 0) : 1; }
+  { const char* v = getenv("BSB_HOST_SPLIT"); e->host_split = v ? (atoi(v) != 0) : 1; }
   { const char* v = getenv("BSB_HOST_STAGE_ACTIONS"); e->host_stage_actions = v ? (atoi(v) != 0) : 1; }
   e->h2d_stream = nullptr; e->h2d_event = nullptr;
   e->early_inflight = false;
@@ -982,7 +993,7 @@ int32_t bsb_step_host(bsb_env* env, const int32_t* actions, const bsb_outputs* h
             BSB_CUDA(cudaStreamWaitEvent(zs, env->h2d_event, 0));
             f.actions = env->h2d_actions;
           }
-          int lrc = mailbox_launch(env, ticket, env->steps_done, &f, false);
+          int lrc = mailbox_launch(env, ticket, env->steps_done, &f, false, (flags & BSB_HOST_NO_WAIT) != 0);
           if (lrc != BSB_OK) return lrc;
         }
         if ((flags & BSB_HOST_FENCE_CALLER) && env->early_inflight) {

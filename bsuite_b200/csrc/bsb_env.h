@@ -74,6 +74,7 @@ struct bsb_env {
   unsigned long long pending_ticket;  // pre-launched launch waiting for its doorbell (0 = none); it is for step steps_done
   unsigned long long doorbell_timeout_ns;
   int host_spin;                      // BSB_HOST_SPIN (default 1): completion through the mailbox instead of a synchronise
+  int host_split;                     // BSB_HOST_SPLIT (default 1): BSB_HOST_NO_WAIT two-phase steps run as two launches (transitions, observations)
   int host_early;                     // BSB_HOST_EARLY (default 1): two-phase host steps (scalars first) where the family allows
   bool early_inflight;                // a two-phase host step may still be streaming observations on copy_stream
   int host_stage_actions;             // BSB_HOST_STAGE_ACTIONS (default 1): two-phase steps get their actions by DMA on a side stream instead of reading them in place

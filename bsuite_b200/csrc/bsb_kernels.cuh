@@ -86,6 +86,9 @@ struct LaunchArgs {
   int32_t wait_doorbell;             // 1: pre-launched -- poll the doorbell for `ticket`, then take the buffers from the mailbox
   unsigned long long doorbell_timeout_ns;
   int32_t* bad_action;      // pinned host flag (device alias): set to 1 when an action is outside [0, num_actions)
+  int32_t phase;            // two-phase host step split over TWO launches (BSB_HOST_NO_WAIT): 1 = transitions + copiers
+                            // only (no shared memory: co-resident with another handle's observation stream),
+                            // 2 = observations only (waits for mail->phase1 == ticket, not for launch 1 to END); 0 = one launch
 };
 
 // Host <-> device mailbox of the doorbell mode.  The host fills `in` and then stores `doorbell = ticket` (release
@@ -554,7 +557,9 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
   }
   // Wait for the previous step's kernel (it wrote the lane state read below), THEN allow the next step's kernel
   // to become resident: its CTAs park at their own wait, so at most one dependent grid is ever pending.
-  if (a.use_pdl) { pdl_wait(); pdl_launch_dependents(); }
+  // (The observation-only launch of a split host step must not wait for its predecessor -- the transitions launch,
+  // whose copiers are still shipping scalars over PCIe -- to END: it waits for that launch's phase-1 flag below.)
+  if (a.use_pdl) { if (a.phase != 2) pdl_wait(); pdl_launch_dependents(); }
   int64_t step0 = a.step0;
   if (a.clock) step0 += (int64_t)*reinterpret_cast<volatile unsigned long long*>(a.clock + 16 * (blockIdx.x % CLOCK_GROUPS));
 
@@ -877,7 +882,7 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
       __syncthreads();
       if (threadIdx.x == 0) atomicAdd(&a.mail->finished, 1ull);
       bool mine = true;
-      int64_t c = own;
+      int64_t c = a.phase == 1 ? n_chunks : own;      // split step: the observations are the next launch's
       while (c < n_chunks) {
         const int64_t warp_base = c * cl;
         const int n_lanes = (B - warp_base) < cl ? (int)(B - warp_base) : cl;
@@ -900,6 +905,28 @@ __global__ void __launch_bounds__(128, BSB_LAUNCH_MIN_BLOCKS(F)) transition_kern
         c = dynamic ? fetch_chunk() : n_chunks;
       }
       cur_chunk = n_chunks;                  // nothing left for the ordinary loop
+    } else if (a.phase == 2) {
+      // Observation-only launch of a split host step: the transitions launch ahead of it in the stream stored every
+      // lane's state and raised mail->phase1; render from the stored state, chunks dealt as usual.
+      if (tid == 0) while (a.mail->phase1 != a.ticket) {}
+      __syncwarp();
+      __threadfence();                       // acquire
+      int64_t c = cur_chunk;
+      while (c < n_chunks) {
+        const int64_t warp_base = c * cl;
+        const int n_lanes = (B - warp_base) < cl ? (int)(B - warp_base) : cl;
+        const int64_t lane = warp_base + tid;
+        const bool active = tid < n_lanes;
+        typename F::Lane L;
+        F::init(p, L);
+        if (active) { F::load(p, lane, L); F::describe(p, L); }
+        const bool bulk = chunk_is_bulk(n_lanes);
+        any_bulk = any_bulk || bulk;
+        R unused_rng;
+        emit_obs(L, unused_rng, io.obs, warp_base, n_lanes, lane, active, bulk);
+        c = dynamic ? fetch_chunk() : n_chunks;
+      }
+      cur_chunk = n_chunks;
     }
   }
 
