@@ -527,47 +527,78 @@ def engine_main(args):
   e2e_value, e2e_windows = timed_e2e(Ke, host_small, WINDOWS, prelaunch=False)
   e2e_prelaunch, _ = timed_e2e(Ke, host_small, 3, prelaunch=True)
 
-  # The strict loop over TWO half-batches driven alternately (rollouts.HostHalves): each half's next actions are
-  # submitted only after ITS previous results have landed, while the other half's kernel has the GPU.
+  # The strict loop over TWO (or three, four) part-batches driven round-robin (rollouts.HostHalves / HostParts): each
+  # part's next actions are submitted only after ITS previous results have landed, while the other parts' kernels
+  # have the GPU.
   halves_value, halves_windows = None, None
+  parts_values, parts_errors = {}, {}
+  best_parts, best_parts_value, best_parts_windows = None, None, None
   if not args.skip_halves:
     from bsuite_b200 import rollouts
-    halves = rollouts.HostHalves(BSUITE_ID, B, device=device, seed=0, lane_offset=rank * B, track_episodes=not args.no_track)
-    split = halves.sizes[0]
-    half_rows = [[r for r in host_actions[:, :split].contiguous().pin_memory()],
-                 [r for r in host_actions[:, split:].contiguous().pin_memory()]]
-    halves.reset()
-
-    def halves_loop(n):
-      halves.submit(0, half_rows[0][0]); halves.submit(1, half_rows[1][0])
-      for t in range(1, n):
-        halves.collect(0); halves.submit(0, half_rows[0][t % Ke])
-        halves.collect(1); halves.submit(1, half_rows[1][t % Ke])
-      halves.collect(0); halves.collect(1)
-
-    halves_loop(10)
-    secs = []
-    for _ in range(WINDOWS):
+    for n_parts in args.e2e_parts:
+      group = None
       if world > 1:
-        dist.barrier()
-      torch.cuda.synchronize()
-      t0 = time.perf_counter()
-      halves_loop(Ke)
-      torch.cuda.synchronize()
-      secs.append(time.perf_counter() - t0)
-    dt = torch.tensor(secs, dtype=torch.float64, device=device)
-    if world > 1:
-      dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    halves_value = world * B * Ke / _median([float(x) for x in dt])
-    halves_windows = [world * B * Ke / float(x) for x in dt]
-    halves.close()
-    del halves, half_rows
-    torch.cuda.empty_cache()
+        dist.barrier()          # the ranks run the leg side by side (it holds no collective of its own)
+      try:      # an optional leg must not take the line down; no collective runs while a part may have failed
+        group = rollouts.HostParts(BSUITE_ID, B, device=device, seed=0, lane_offset=rank * B, parts=n_parts,
+                                   track_episodes=not args.no_track)
+        bounds = [0]
+        for size in group.sizes:
+          bounds.append(bounds[-1] + size)
+        part_rows = [[r for r in host_actions[:, bounds[i]:bounds[i + 1]].contiguous().pin_memory()]
+                     for i in range(n_parts)]
+        group.reset()
+
+        def parts_loop(n):
+          for i in range(n_parts):
+            group.submit(i, part_rows[i][0])
+          for t in range(1, n):
+            row = t % Ke
+            for i in range(n_parts):
+              group.collect(i); group.submit(i, part_rows[i][row])
+          for i in range(n_parts):
+            group.collect(i)
+
+        parts_loop(30)
+        secs = []
+        for _ in range(WINDOWS):
+          torch.cuda.synchronize()
+          t0 = time.perf_counter()
+          parts_loop(Ke)
+          torch.cuda.synchronize()
+          secs.append(time.perf_counter() - t0)
+        local = secs
+      except Exception as err:      # pylint: disable=broad-except
+        parts_errors[str(n_parts)] = repr(err)[:200]
+        local = None
+      finally:
+        if group is not None:
+          try:
+            group.close()
+          except Exception:      # pylint: disable=broad-except
+            pass
+        group = None
+        part_rows = None
+        torch.cuda.empty_cache()
+      # every rank joins the reduction, failed or not (a rank that failed reports no time: the leg is dropped)
+      dt = torch.tensor(local if local is not None else [float('inf')] * WINDOWS, dtype=torch.float64, device=device)
+      if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+      times = [float(x) for x in dt]
+      if all(x != float('inf') for x in times):
+        value_n = world * B * Ke / _median(times)
+        windows_n = [world * B * Ke / x for x in times]
+        parts_values[str(n_parts)] = value_n
+        if n_parts == 2:
+          halves_value, halves_windows = value_n, windows_n
+        if best_parts_value is None or value_n > best_parts_value:
+          best_parts, best_parts_value, best_parts_windows = n_parts, value_n, windows_n
   strict_value, strict_windows = e2e_value, e2e_windows
   e2e_mode = 'one batch: step_host per step'
-  if halves_value is not None and halves_value > e2e_value:
-    e2e_value, e2e_windows = halves_value, halves_windows
-    e2e_mode = 'two half-batches driven alternately (rollouts.HostHalves), each half a strict loop'
+  if best_parts_value is not None and best_parts_value > e2e_value:
+    e2e_value, e2e_windows = best_parts_value, best_parts_windows
+    e2e_mode = (f'{best_parts} part-batches driven round-robin (rollouts.HostParts'
+                f'{" = HostHalves" if best_parts == 2 else ""}), each part a strict loop')
 
   # The same host-memory traffic WITHOUT a host synchronise per step (actions that do not depend on the previous
   # result, as in this random-action workload): env.step() given a pinned host action tensor and outputs whose
@@ -703,10 +734,11 @@ def engine_main(args):
                 'steps': Ke, 'windows': e2e_windows, 'mode': e2e_mode,
                 'one_batch_value': strict_value, 'one_batch_windows': strict_windows,
                 'two_halves_value': halves_value, 'two_halves_windows': halves_windows,
+                'parts_values': parts_values, 'parts_errors': parts_errors or None,
                 'prelaunch_value': e2e_prelaunch,
                 'host_obs_value': host_obs_value, 'pipelined_value': e2e_pipelined,
                 'host_obs_d2h_bytes_per_step': 4 * B * SIZE * SIZE + 12 * B,
-                'note': 'value = the faster of one_batch_value and two_halves_value (mode says which); both are the strict '
+                'note': 'value = the fastest of one_batch_value and parts_values (mode says which; parts_values[\"2\"] = two_halves_value); all are the strict '
                         'host loop -- the next actions of a lane are submitted only after that lane\'s previous reward / '
                         'discount / step_type have landed in host memory -- with the same bytes over PCIe per step. '
                         'two_halves_value: the lanes split over two handles (lane keys continue across the split) that '
@@ -739,7 +771,9 @@ def engine_main(args):
 def main():
   parser = argparse.ArgumentParser()
   parser.add_argument('--gpus', type=int, default=1)
-  parser.add_argument('--skip-halves', action='store_true', help='skip the two-half-batches e2e leg')
+  parser.add_argument('--skip-halves', action='store_true', help='skip the part-batches e2e legs')
+  parser.add_argument('--e2e-parts', type=int, nargs='*', default=[2, 3, 4],
+                      help='part counts of the part-batches e2e legs (rollouts.HostParts)')
   parser.add_argument('--steps', type=int, default=400)
   parser.add_argument('--warmup', type=int, default=20)
   parser.add_argument('--impl', default='b200', choices=['b200', 'reference'])

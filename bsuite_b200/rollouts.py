@@ -8,9 +8,9 @@
   * `Trajectory` / `collect` -- the `[T + 1]` observations / `[T]` actions, rewards, discounts layout of
     `bsuite/baselines/utils/sequence.py:26-35`, as device tensors with a lane axis, filled by ONE fused rollout
     (`bsb_rollout`: on-device uniform random actions) instead of T appends.
-  * `HostHalves` -- the reference's strict host loop (one decision per `env.step`, experiment.py:45-57) over two
-    half-batches driven alternately, so that one half's PCIe round trip and decision hide behind the other half's
-    kernel.
+  * `HostParts` / `HostHalves` -- the reference's strict host loop (one decision per `env.step`,
+    experiment.py:45-57) over two (or more) part-batches driven round-robin, so that one part's PCIe round trip and
+    decision hide behind the other parts' kernels.
 """
 
 from typing import Any, NamedTuple, Optional
@@ -143,86 +143,120 @@ class Replay:
     return self.size / self._capacity
 
 
-class HostHalves:
-  """`batch` lanes of one experiment as TWO half-batch environments that a HOST-side agent drives alternately.
+class HostParts:
+  """`batch` lanes of one experiment as `parts` environments that a HOST-side agent drives round-robin.
 
   The reference's loop is strict: the agent acts on what the previous `env.step` returned (experiment.py:45-57).
   With the policy on the host, every step of one big batch leaves the GPU idle while reward / discount / step_type
   cross PCIe, the agent decides and the next actions come back.  Lanes are independent, so the batch
-  is split in two handles (lane keys continue across the split: the trajectories are those of ONE `batch`-lane
-  environment, bit for bit) and each half stays a strict loop of its own -- `submit(h, actions)` enqueues half h's
-  step (`BSB_HOST_NO_WAIT`), `collect(h)` returns its host timestep -- while the OTHER half's kernel has the GPU:
+  is split over `parts` handles (lane keys continue across the splits: the trajectories are those of ONE
+  `batch`-lane environment, bit for bit) and each part stays a strict loop of its own -- `submit(p, actions)`
+  enqueues part p's step (`BSB_HOST_NO_WAIT`), `collect(p)` returns its host timestep -- while the OTHER parts'
+  kernels have the GPU:
 
-      halves.submit(0, a0); halves.submit(1, a1)
+      for p in range(parts): halves.submit(p, a[p])
       while ...:
-        ts0, obs0 = halves.collect(0); halves.submit(0, policy(ts0))
-        ts1, obs1 = halves.collect(1); halves.submit(1, policy(ts1))
+        for p in range(parts):
+          ts, obs = halves.collect(p); halves.submit(p, policy(ts))
 
-  `run(policy, num_steps)` is that loop.  Needs a CUDA device (pinned buffers); host environments gain nothing
-  from it and are refused.
+  `run(policy, num_steps)` is that loop.  Two parts (`HostHalves`) hide one part's round trip behind the other's
+  kernel; more parts give every round trip more kernels to hide behind at the price of more (smaller) launches and
+  host calls per step.  Needs a CUDA device (pinned buffers); host environments gain nothing from it and are refused.
   """
 
   def __init__(self, bsuite_id: str, batch: int, device='cuda', seed: Optional[int] = None, lane_offset: int = 0,
-               **engine_kwargs):
+               parts: int = 2, **engine_kwargs):
     from bsuite_b200 import registry
-    batch = int(batch)
-    if batch < 2:
-      raise ValueError('HostHalves needs at least two lanes')
-    first = (batch // 2 + 31) // 32 * 32 if batch >= 64 else batch // 2     # whole warps in the first half
+    batch, parts = int(batch), int(parts)
+    if parts < 2:
+      raise ValueError('HostParts needs at least two parts')
+    if batch < parts:
+      raise ValueError(f'HostParts needs at least one lane per part ({parts} parts, {batch} lanes)')
+    self.sizes = split_sizes(batch, parts)
     kwargs = dict(engine_kwargs)
     if seed is not None:
       kwargs['seed'] = seed
-    self.envs = [registry.load_from_id(bsuite_id, batch=first, device=device, lane_offset=lane_offset, **kwargs),
-                 registry.load_from_id(bsuite_id, batch=batch - first, device=device, lane_offset=lane_offset + first,
-                                       **kwargs)]
-    if any(e.device.type != 'cuda' for e in self.envs):
+    self.envs, offset = [], int(lane_offset)
+    try:
+      for size in self.sizes:
+        self.envs.append(registry.load_from_id(bsuite_id, batch=size, device=device, lane_offset=offset, **kwargs))
+        offset += size
+      if any(e.device.type != 'cuda' for e in self.envs):
+        raise ValueError('HostParts drives CUDA environments from pinned host buffers')
+    except Exception:
       for e in self.envs:
         e.close()
-      raise ValueError('HostHalves drives CUDA environments from pinned host buffers')
-    self.batch, self.sizes = batch, (first, batch - first)
+      raise
+    self.batch, self.parts = batch, parts
     self.host = [e.make_host_buffers() for e in self.envs]
     self.out = [e.make_buffers() for e in self.envs]
-    self._in_flight = [False, False]
+    self._in_flight = [False] * parts
 
   def reset(self):
-    """Resets both halves; returns their device TimeSteps."""
+    """Resets every part; returns their device TimeSteps."""
     self.drain()
     return [e.reset(out=o) for e, o in zip(self.envs, self.out)]
 
-  def submit(self, half: int, actions):
-    """Enqueues one step of `half` with `actions` (pinned CPU int32 [sizes[half]]); returns at once."""
-    if self._in_flight[half]:
-      raise RuntimeError(f'half {half} already has a step in flight: collect() it first')
-    self.envs[half].step_host(actions, self.host[half], self.out[half], wait=False)
-    self._in_flight[half] = True
+  def submit(self, part: int, actions):
+    """Enqueues one step of `part` with `actions` (pinned CPU int32 [sizes[part]]); returns at once."""
+    if self._in_flight[part]:
+      raise RuntimeError(f'part {part} already has a step in flight: collect() it first')
+    self.envs[part].step_host(actions, self.host[part], self.out[part], wait=False)
+    self._in_flight[part] = True
 
-  def collect(self, half: int):
-    """Waits for the step of `half` in flight; returns (host TimeStep, device observation)."""
-    self.envs[half].host_wait()
-    self._in_flight[half] = False
-    return self.host[half].timestep(), self.out[half].observation
+  def collect(self, part: int):
+    """Waits for the step of `part` in flight; returns (host TimeStep, device observation)."""
+    self.envs[part].host_wait()
+    self._in_flight[part] = False
+    return self.host[part].timestep(), self.out[part].observation
 
   def drain(self):
-    for half in (0, 1):
-      if self._in_flight[half]:
-        self.collect(half)
+    for part in range(self.parts):
+      if self._in_flight[part]:
+        self.collect(part)
 
   def run(self, policy, num_steps: int, first_actions=None):
-    """`num_steps` steps of every lane: `policy(half, step, host_timestep) -> pinned int32 actions` is asked once
-    per half and step, always with that half's LATEST timestep (None before the first step unless
-    `first_actions` = [actions0, actions1] is given).  Returns the final host timesteps of both halves."""
-    last = [None, None]
-    for half in (0, 1):
-      self.submit(half, first_actions[half] if first_actions is not None else policy(half, 0, None))
+    """`num_steps` steps of every lane: `policy(part, step, host_timestep) -> pinned int32 actions` is asked once
+    per part and step, always with that part's LATEST timestep (None before the first step unless
+    `first_actions` = [actions of part 0, ...] is given).  Returns the final host timesteps of the parts."""
+    last = [None] * self.parts
+    for part in range(self.parts):
+      self.submit(part, first_actions[part] if first_actions is not None else policy(part, 0, None))
     for step in range(1, int(num_steps)):
-      for half in (0, 1):
-        last[half] = self.collect(half)[0]
-        self.submit(half, policy(half, step, last[half]))
-    for half in (0, 1):
-      last[half] = self.collect(half)[0]
+      for part in range(self.parts):
+        last[part] = self.collect(part)[0]
+        self.submit(part, policy(part, step, last[part]))
+    for part in range(self.parts):
+      last[part] = self.collect(part)[0]
     return last
 
   def close(self):
     self.drain()
     for e in self.envs:
       e.close()
+
+
+def split_sizes(batch: int, parts: int):
+  """Lanes per part: whole warps (multiples of 32 lanes) in every part but the last when there are enough lanes,
+  sizes as equal as that allows; `sum == batch`, every part non-empty."""
+  batch, parts = int(batch), int(parts)
+  if batch >= 64 * parts:
+    warps = (batch + 31) // 32
+    per, extra = divmod(warps, parts)
+    sizes = [(per + (1 if i < extra else 0)) * 32 for i in range(parts)]
+    sizes[-1] = batch - sum(sizes[:-1])
+  else:
+    per, extra = divmod(batch, parts)
+    sizes = [per + (1 if i < extra else 0) for i in range(parts)]
+  assert sum(sizes) == batch and all(size > 0 for size in sizes), (batch, parts, sizes)
+  return tuple(sizes)
+
+
+class HostHalves(HostParts):
+  """`HostParts` with two parts: one half's PCIe round trip and decision hide behind the other half's kernel."""
+
+  def __init__(self, bsuite_id: str, batch: int, device='cuda', seed: Optional[int] = None, lane_offset: int = 0,
+               **engine_kwargs):
+    if int(batch) < 2:
+      raise ValueError('HostHalves needs at least two lanes')
+    super().__init__(bsuite_id, batch, device=device, seed=seed, lane_offset=lane_offset, parts=2, **engine_kwargs)

@@ -335,3 +335,58 @@ def test_host_halves_refuses_host_environments():
   from bsuite_b200 import rollouts
   with pytest.raises(ValueError):
     rollouts.HostHalves('catch/0', 64, device='cpu')
+  with pytest.raises(ValueError):
+    rollouts.HostParts('catch/0', 64, device='cpu', parts=3)
+  with pytest.raises(ValueError):
+    rollouts.HostParts('catch/0', 64, device='cpu', parts=1)
+  with pytest.raises(ValueError):
+    rollouts.HostParts('catch/0', 2, device='cpu', parts=3)
+
+
+@pytest.mark.parametrize('batch,parts', [(65536, 2), (65536, 3), (65536, 4), (8229, 3), (300, 3), (2, 2), (5, 4), (127, 2), (100, 3)])
+def test_parts_cover_the_batch_in_whole_warps(batch, parts):
+  from bsuite_b200 import rollouts
+  sizes = rollouts.split_sizes(batch, parts)
+  assert len(sizes) == parts and sum(sizes) == batch and min(sizes) > 0
+  if batch >= 64 * parts:
+    assert all(size % 32 == 0 for size in sizes[:-1]) and max(sizes) - min(sizes) <= 63
+  else:
+    assert max(sizes) - min(sizes) <= 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('bsuite_id,batch,parts', [('deep_sea/11', 8192 + 37, 3), ('deep_sea/11', 4096, 4), ('catch/0', 1000, 3)])
+def test_more_than_two_parts_driven_round_robin_are_one_batch(bsuite_id, batch, parts):
+  """rollouts.HostParts with 3 / 4 handles: one step in flight on each, collected round-robin; every lane's trajectory
+  is the one it has in a single `batch`-lane environment."""
+  from bsuite_b200 import rollouts
+  T = 20
+  group = rollouts.HostParts(bsuite_id, batch, device='cuda', seed=5, track_episodes=True, parts=parts)
+  whole = bsuite_b200.load_from_id(bsuite_id, batch=batch, device='cuda', seed=5, track_episodes=True)
+  assert sum(group.sizes) == batch and len(group.envs) == parts
+  bounds = np.concatenate([[0], np.cumsum(group.sizes)])
+  assert [e.lane_offset for e in group.envs] == list(bounds[:-1])
+  actions = torch.as_tensor(np.random.RandomState(3).randint(whole.num_actions, size=(T, batch)).astype(np.int32))
+  pinned = [actions[:, bounds[p]:bounds[p + 1]].contiguous().pin_memory() for p in range(parts)]
+  group.reset(); whole.reset()
+  want = [whole.step(actions[t].cuda(), out=whole.make_buffers()) for t in range(T)]
+  torch.cuda.synchronize()
+
+  def check(part, t, ts, obs):
+    lanes = slice(int(bounds[part]), int(bounds[part + 1]))
+    for field in ('step_type', 'reward', 'discount'):
+      np.testing.assert_array_equal(_np(getattr(ts, field)), _np(getattr(want[t], field))[lanes], err_msg=f'{field} part={part} t={t}')
+    torch.cuda.synchronize()
+    assert torch.equal(obs, want[t].observation[lanes]), (part, t)
+
+  for part in range(parts):
+    group.submit(part, pinned[part][0])
+  for t in range(1, T):
+    for part in range(parts):
+      check(part, t - 1, *group.collect(part))
+      group.submit(part, pinned[part][t])
+  for part in range(parts):
+    check(part, T - 1, *group.collect(part))
+  sums = sum(e.episode_stat_sums() for e in group.envs)
+  np.testing.assert_allclose(_np(sums), _np(whole.episode_stat_sums()), rtol=1e-12)
+  group.close(); whole.close()
