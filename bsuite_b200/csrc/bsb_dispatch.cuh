@@ -127,6 +127,7 @@ int device_launch(bsb_env* e, LaunchArgs a, cudaStream_t stream) {
     int m = 1;
     while (m < 16 && (size_t)(2 * m) * tile <= 40 * 1024) m <<= 1;
     if (e->deep_sea_group > 0) m = e->deep_sea_group;
+    if (a.phase == 2 && e->split_group > 0) m = e->split_group;      // observation-only launch of a split host step
     if (m > chunk) m = chunk;               // a group never spans chunks
     if (((size_t)m * tile) % 16 != 0 || (size_t)TILE_STAGES * m * tile > 100 * 1024) {
       a.emit_bulk = 0;                      // tiles too large (or misaligned) for the staged path: vector stores
@@ -183,8 +184,11 @@ int device_launch(bsb_env* e, LaunchArgs a, cudaStream_t stream) {
   if (persistent) {
     // As many CTAs as are co-resident (shared-memory bound; 1 KB per CTA is reserved by the driver); their warps
     // draw chunks from the environment's global counter.
-    const int64_t per_sm = (int64_t)((227 * 1024) / (smem + 1024));
-    const int64_t resident = (int64_t)e->num_sms * (per_sm < 1 ? 1 : (per_sm > 16 ? 16 : per_sm));
+    int64_t per_sm = (int64_t)((227 * 1024) / (smem + 1024));
+    per_sm = per_sm < 1 ? 1 : (per_sm > 16 ? 16 : per_sm);
+    // observation-only launch of a split host step: leave room for ANOTHER handle's observation stream on every SM
+    if (a.phase == 2 && e->split_ctas_per_sm > 0 && per_sm > e->split_ctas_per_sm) per_sm = e->split_ctas_per_sm;
+    const int64_t resident = (int64_t)e->num_sms * per_sm;
     if (grid > resident) {
       grid = resident;
       a.work_counter = a.clock ? a.clock + CLOCK_CHUNK : e->work_counter;

@@ -496,6 +496,10 @@ int32_t bsb_create(const bsb_config* config, int64_t batch, int32_t device, uint
   { const char* v = getenv("BSB_HOST_SPIN"); e->host_spin = v ? (atoi(v) != 0) : 1; }
   { const char* v = getenv("BSB_HOST_EARLY"); e->host_early = v ? (atoi(v) != 0) : 1; }
   { const char* v = getenv("BSB_HOST_SPLIT"); e->host_split = v ? (atoi(v) != 0) : 1; }
+  { const char* v = getenv("BSB_SPLIT_GROUP"); e->split_group = v ? atoi(v) : 0;
+    if (e->split_group < 0 || e->split_group > 32 || (e->split_group & (e->split_group - 1))) e->split_group = 0; }
+  { const char* v = getenv("BSB_SPLIT_CTAS_PER_SM"); e->split_ctas_per_sm = v ? atoi(v) : 0;
+    if (e->split_ctas_per_sm < 0 || e->split_ctas_per_sm > 16) e->split_ctas_per_sm = 0; }
   { const char* v = getenv("BSB_HOST_STAGE_ACTIONS"); e->host_stage_actions = v ? (atoi(v) != 0) : 1; }
   e->h2d_stream = nullptr; e->h2d_event = nullptr;
   e->early_inflight = false;

@@ -75,6 +75,9 @@ struct bsb_env {
   unsigned long long doorbell_timeout_ns;
   int host_spin;                      // BSB_HOST_SPIN (default 1): completion through the mailbox instead of a synchronise
   int host_split;                     // BSB_HOST_SPLIT (default 1): BSB_HOST_NO_WAIT two-phase steps run as two launches (transitions, observations)
+  int split_group;                    // BSB_SPLIT_GROUP (default 0 = as ordinary steps): lanes per bulk store of the observation-only launch of a split step
+  int split_ctas_per_sm;              // BSB_SPLIT_CTAS_PER_SM (default 0 = no cap): persistent CTAs per SM of that launch, so that the
+                                      // observation streams of two handles can be co-resident (shared memory) instead of taking turns
   int host_early;                     // BSB_HOST_EARLY (default 1): two-phase host steps (scalars first) where the family allows
   bool early_inflight;                // a two-phase host step may still be streaming observations on copy_stream
   int host_stage_actions;             // BSB_HOST_STAGE_ACTIONS (default 1): two-phase steps get their actions by DMA on a side stream instead of reading them in place

@@ -11,6 +11,46 @@ sys.path.insert(0, ROOT)
 import torch
 import bsuite_b200
 
+
+def split_steps():
+  """Split host steps (BSB_HOST_NO_WAIT: transitions + copiers, then the observation-only launch that waits for the
+  phase-1 flag) on 2 / 3 handles driven round-robin, against one ordinary environment."""
+  from bsuite_b200 import rollouts
+  for bsuite_id, batch, parts in (('deep_sea/11', 12000 + 5, 3), ('deep_sea_stochastic/3', 9000, 2)):
+    group = rollouts.HostParts(bsuite_id, batch, device='cuda', seed=3, track_episodes=True, parts=parts)
+    twin = bsuite_b200.load_from_id(bsuite_id, batch=batch, device='cuda', seed=3, track_episodes=True)
+    bounds = [0]
+    for size in group.sizes:
+      bounds.append(bounds[-1] + size)
+    T = 5
+    acts = torch.as_tensor(twin.random_actions(T, action_seed=1, first_step=0))
+    rows = [acts[:, bounds[p]:bounds[p + 1]].contiguous().pin_memory() for p in range(parts)]
+    group.reset(); twin.reset()
+    want = [twin.step(acts[t].cuda(), out=twin.make_buffers()) for t in range(T)]
+    torch.cuda.synchronize()
+
+    def check(p, t, ts, obs):
+      lanes = slice(bounds[p], bounds[p + 1])
+      torch.cuda.synchronize()
+      assert torch.equal(obs, want[t].observation[lanes]) and torch.equal(ts.reward, want[t].reward.cpu()[lanes]) \
+          and torch.equal(ts.step_type, want[t].step_type.cpu()[lanes]), (p, t)
+
+    for p in range(parts):
+      group.submit(p, rows[p][0])
+    for t in range(1, T):
+      for p in range(parts):
+        check(p, t - 1, *group.collect(p)); group.submit(p, rows[p][t])
+    for p in range(parts):
+      check(p, T - 1, *group.collect(p))
+    print(bsuite_id, batch, f'{parts} parts, split host steps == ordinary steps: True', flush=True)
+    group.close(); twin.close()
+
+
+if '--only-split' in sys.argv:
+  split_steps()
+  print('sanitize workload (split steps) finished')
+  sys.exit(0)
+
 for bsuite_id, batch in (('deep_sea/11', 20000), ('deep_sea_stochastic/3', 40001), ('catch_noise/0', 5000), ('cartpole/0', 3000),
                          ('umbrella_length/3', 2000), ('umbrella_distract/22', 1500), ('mnist/0', 1500), ('mnist/0', 30000)):
   if bsuite_id.startswith('mnist'):
@@ -62,6 +102,7 @@ for bsuite_id, batch in (('deep_sea/11', 20000), ('catch/0', 3000), ('mnist/0', 
   assert env.invalid_actions_seen() and torch.equal(env.episode_stat_sums(), twin.episode_stat_sums())
   print(bsuite_id, batch, 'host-driven steps == ordinary steps: True', flush=True)
   env.close(); twin.close()
+split_steps()
 # One-launch reduction over several environments and a whole lock-step in one graph.
 from bsuite_b200 import suite
 ids = ['catch/0', 'deep_sea/0', 'bandit_noise/0', 'cartpole/0', 'mnist/0', 'umbrella_length/0']
