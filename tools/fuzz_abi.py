@@ -83,11 +83,16 @@ def main():
       hostile[rng.randrange(batch)] = rng.choice([-1, n_act.value, 255, 1 << 20, -(1 << 31), (1 << 31) - 1])
       assert lib.bsb_step(handle, ctypes.c_void_p(hostile.ctypes.data), ctypes.byref(out), None) != 0
       assert lib.bsb_rollout(handle, T, ctypes.c_void_p(hostile.ctypes.data), 0, ctypes.byref(out), None, None) != 0
-      assert lib.bsb_step_host(handle, ctypes.c_void_p(hostile.ctypes.data), ctypes.byref(out), None, None, rng.choice([0, 1, 2, 4, 7])) != 0
+      assert lib.bsb_step_host(handle, ctypes.c_void_p(hostile.ctypes.data), ctypes.byref(out), None, None, rng.choice([0, 1, 2, 4, 7, 8, 10, 12, 15])) != 0
       seen = ctypes.c_int32(7)
       assert lib.bsb_invalid_actions(handle, ctypes.byref(seen)) == 0 and seen.value == 0
       assert lib.bsb_step_host(handle, ctypes.c_void_p(acts.ctypes.data), ctypes.byref(out), None, None, rng.choice([0, 1, 2, 4, 7])) == 0
       assert lib.bsb_host_flush(handle) == 0
+      # ABI v6: a host environment has nothing to wait for -- BSB_HOST_NO_WAIT is simply synchronous there, and
+      # bsb_host_wait is a no-op on a handle without a step in flight (and refuses a null handle)
+      assert lib.bsb_step_host(handle, ctypes.c_void_p(acts.ctypes.data), ctypes.byref(out), None, None, rng.choice([8, 9, 12])) == 0
+      assert lib.bsb_host_wait(handle) == 0 and lib.bsb_host_wait(handle) == 0
+      assert lib.bsb_host_wait(None) != 0
       for _ in range(4):
         lib.bsb_step(handle, ctypes.c_void_p(acts.ctypes.data), ctypes.byref(out), None)
         lib.bsb_rollout(handle, T, ctypes.c_void_p(acts.ctypes.data) if rng.random() < 0.5 else None, rng.getrandbits(64),
