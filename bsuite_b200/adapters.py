@@ -62,57 +62,55 @@ def _spaces():
     return Discrete, Box
 
 
+def _bounds(spec) -> Tuple[Any, Any]:
+  """(low, high) of a dm_env spec: its own bounds when it has them, the whole real line otherwise."""
+  if isinstance(spec, specs.BoundedArray):
+    return spec.minimum, spec.maximum
+  return -float('inf'), float('inf')
+
+
 class GymAdapter:
-  """Wraps a dm_env-style environment (e.g. `bsuite_b200.load_from_id(id)`) in the gym call convention."""
+  """The gym call convention (`reset() -> obs`, `step(a) -> (obs, reward, done, info)`) over a dm_env-style
+  environment such as `bsuite_b200.load_from_id(id)`; same surface as `GymFromDMEnv` (gym_wrapper.py:30-100).
+
+  The specs of an environment do not change, so the three spaces are built once, here; the latest TimeStep is kept
+  whole (`render` shows its observation, `game_over` -- the attribute Dopamine agents poll, gym_wrapper.py:39 -- is
+  whether it was LAST).  Anything else is looked up on the wrapped environment."""
 
   metadata = {'render.modes': ['human', 'rgb_array']}
 
   def __init__(self, env):
-    self._env = env
-    self._last_observation = None
-    self.viewer = None
-    self.game_over = False            # read by Dopamine agents (gym_wrapper.py:39)
+    discrete, box = _spaces()
+    observation_spec = env.observation_spec()
+    low, high = _bounds(observation_spec)
+    self._env, self._timestep, self.viewer = env, None, None
+    self.action_space = discrete(env.action_spec().num_values)
+    self.observation_space = box(low=float(low), high=float(high), shape=observation_spec.shape,
+                                 dtype=observation_spec.dtype)
+    self.reward_range = _bounds(env.reward_spec())
 
-  def step(self, action: int) -> Tuple[np.ndarray, float, bool, Dict[str, Any]]:
-    timestep = self._env.step(action)
-    self._last_observation = timestep.observation
-    if timestep.last():
-      self.game_over = True
-    return timestep.observation, timestep.reward or 0., timestep.last(), {}
+  @property
+  def game_over(self) -> bool:
+    return self._timestep is not None and self._timestep.last()
 
   def reset(self) -> np.ndarray:
-    self.game_over = False
-    timestep = self._env.reset()
-    self._last_observation = timestep.observation
-    return timestep.observation
+    self._timestep = self._env.reset()
+    return self._timestep.observation
+
+  def step(self, action: int) -> Tuple[np.ndarray, float, bool, Dict[str, Any]]:
+    self._timestep = ts = self._env.step(action)
+    return ts.observation, (0. if ts.reward is None else ts.reward), ts.last(), {}
 
   def render(self, mode: str = 'rgb_array'):
-    if self._last_observation is None:
+    if mode != 'rgb_array':
+      raise NotImplementedError('only the rgb_array render mode is available (no display here)')
+    if self._timestep is None:
       raise ValueError('Environment not ready to render. Call reset() first.')
-    if mode == 'rgb_array':
-      return self._last_observation
-    raise NotImplementedError('only the rgb_array render mode is available (no display here)')
-
-  @property
-  def action_space(self):
-    return _spaces()[0](self._env.action_spec().num_values)
-
-  @property
-  def observation_space(self):
-    spec = self._env.observation_spec()
-    box = _spaces()[1]
-    if isinstance(spec, specs.BoundedArray):
-      return box(low=float(spec.minimum), high=float(spec.maximum), shape=spec.shape, dtype=spec.dtype)
-    return box(low=-float('inf'), high=float('inf'), shape=spec.shape, dtype=spec.dtype)
-
-  @property
-  def reward_range(self) -> Tuple[float, float]:
-    spec = self._env.reward_spec()
-    if isinstance(spec, specs.BoundedArray):
-      return spec.minimum, spec.maximum
-    return -float('inf'), float('inf')
+    return self._timestep.observation
 
   def __getattr__(self, name):
+    if name == '_env':             # not constructed yet (copy / pickle probing): no recursion
+      raise AttributeError(name)
     return getattr(self._env, name)
 
 
