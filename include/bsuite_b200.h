@@ -336,7 +336,10 @@ int32_t bsb_set_state(bsb_env* env, const void* src_host, int64_t nbytes,
  *       those of one big batch) and alternate -- while one half's scalars cross
  *       PCIe and its agent decides, the other half's kernel has the GPU, so each
  *       half remains the reference's strict loop (act on what the previous step
- *       returned) and the GPU is not left idle in between.  Not with
+ *       returned) and the GPU is not left idle in between (two to four handles;
+ *       three measured best on a B200).  Pass BSB_HOST_FENCE_CALLER with it: the
+ *       loop measured 1.5x slower without the fence's event record between a
+ *       handle's observation launch and its next launch.  Not with
  *       BSB_HOST_PRELAUNCH.
  */
 #define BSB_HOST_ORDER_AFTER_STREAM 1u
