@@ -577,6 +577,17 @@ class DmEnvAdapter(dm_env.Environment):
     self._outputs.reward_f64 = self._reward.ctypes.data
     self._outputs.discount = self._discount.ctypes.data
     self._outputs.step_type = self._step_type.ctypes.data
+    # the per-step call passes the same three pointers every time: build their ctypes objects once
+    self._action_ptr = ctypes.c_void_p(self._action.ctypes.data)
+    self._outputs_ref = ctypes.byref(self._outputs)
+    self._step_types = tuple(dm_env.StepType(k) for k in range(3))
+    # ... and read / write the four scalars through ctypes views of the same memory (a numpy scalar index costs more
+    # than the whole bandit transition)
+    self._action_c = ctypes.c_int32.from_address(self._action.ctypes.data)
+    self._reward_c = ctypes.c_double.from_address(self._reward.ctypes.data)
+    self._discount_c = ctypes.c_float.from_address(self._discount.ctypes.data)
+    self._step_type_c = ctypes.c_int32.from_address(self._step_type.ctypes.data)
+    self._obs_view = self._obs.reshape(spec.obs_shape)
     self._dev = None
     self._reset_stream, self._host_flags = None, 0   # the next host step is fenced behind the stream reset() used
     if self._ordinal >= 0:   # device-side scratch for reset(); step() uses bsb_step_host
@@ -589,11 +600,11 @@ class DmEnvAdapter(dm_env.Environment):
           step_type=torch.empty(1, dtype=torch.int32, device=device_t))
 
   def _timestep(self):
-    step_type = dm_env.StepType(int(self._step_type[0]))
-    observation = self._obs.reshape(self._spec.obs_shape).copy()   # caller owns a fresh array
-    if step_type == dm_env.StepType.FIRST:
-      return dm_env.TimeStep(step_type, None, None, observation)
-    return dm_env.TimeStep(step_type, float(self._reward[0]), float(self._discount[0]), observation)
+    code = self._step_type_c.value
+    observation = self._obs_view.copy()                            # caller owns a fresh array
+    if code == 0:                                                  # FIRST: reward and discount are None (dm_env.restart)
+      return dm_env.TimeStep(self._step_types[0], None, None, observation)
+    return dm_env.TimeStep(self._step_types[code], self._reward_c.value, self._discount_c.value, observation)
 
   def reset(self):
     if self._ordinal < 0:
@@ -616,14 +627,15 @@ class DmEnvAdapter(dm_env.Environment):
       # the reference indexes a table with the action and fails with IndexError (bandit.py:61, catch.py:84) or
       # silently takes "the other" branch (deep_sea.py:118); an action_spec violation is an error here
       raise ValueError(f'action {action} is outside the action_spec: DiscreteArray(num_values={self._spec.num_actions})')
-    self._action[0] = action
+    self._action_c.value = action
     if self._ordinal < 0:
-      _lib.check(self._lib.bsb_step(self._handle.ptr, ctypes.c_void_p(self._action.ctypes.data),
-                                    ctypes.byref(self._outputs), None))
+      status = self._lib.bsb_step(self._handle.ptr, self._action_ptr, self._outputs_ref, None)
     else:
-      _lib.check(self._lib.bsb_step_host(self._handle.ptr, ctypes.c_void_p(self._action.ctypes.data),
-                                         ctypes.byref(self._outputs), None, self._reset_stream, self._host_flags))
+      status = self._lib.bsb_step_host(self._handle.ptr, self._action_ptr, self._outputs_ref, None, self._reset_stream,
+                                       self._host_flags)
       self._host_flags = 0
+    if status:
+      _lib.check(status)
     return self._timestep()
 
   def observation_spec(self):
