@@ -17,6 +17,8 @@ MNIST_DIR = os.path.join('/tmp', 'bsb_test_mnist')
 
 def pytest_configure(config):
   config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
+  config.addinivalue_line('markers', 'runs_last: scheduled after every other test of the session (a CUDA fault in it '
+                                     'cannot poison the context of tests that were known to pass)')
 
 
 def _have_cuda() -> bool:
@@ -25,6 +27,7 @@ def _have_cuda() -> bool:
 
 
 def pytest_collection_modifyitems(config, items):
+  items.sort(key=lambda item: 1 if 'runs_last' in item.keywords else 0)      # stable: everything else keeps its order
   if _have_cuda():
     return
   skip = pytest.mark.skip(reason='no CUDA device in this container')

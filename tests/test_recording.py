@@ -230,3 +230,95 @@ def test_batched_log_rows_for_other_families(device, bsuite_id, env_class, kwarg
       for c, v in row.items():
         got = rows[k, list(logged['columns']).index(c), lane]
         assert got == pytest.approx(float(v), abs=1e-6 if env_class == 'cartpole' and device == 'cuda' else 0), (lane, k, c)
+
+
+# ---------------------------------------------------------------------------- CUDA rows against the host path's rows
+# The tests above compare the device-side recorder with the reference's own Logging wrapper, which needs the
+# reference tree: in the build container that pins the HOST path (no GPU there), and on the GPU box (no reference
+# tree there) their CUDA variants are skipped.  These close the chain on the GPU box without the reference: the same
+# `__host__ __device__` recorder on CUDA against the engine's host path, which the tests above pin to the reference.
+# They were written after the round's GPU budget was spent and have not run on a GPU yet: non-strict xfail (an XPASS
+# is the verification, a failure is reported without gating the suite) and scheduled last.
+_FIRST_GPU_RUN = pytest.mark.xfail(strict=False, reason='first run on a GPU: reported, not gating (see the comment above)')
+
+
+@pytest.mark.gpu
+@pytest.mark.runs_last
+@_FIRST_GPU_RUN
+@pytest.mark.parametrize('bsuite_id,batch,steps', [('catch/0', 64, 10000), ('cartpole/0', 6, 3000),
+                                                   ('deep_sea_stochastic/0', 6, 3000), ('bandit_scale/3', 6, 3000),
+                                                   ('deep_sea/11', 70, 4000)])
+def test_device_log_rows_equal_the_host_path_rows(bsuite_id, batch, steps):
+  import torch
+  cuda = bsuite_b200.load_from_id(bsuite_id, batch=batch, device='cuda', seed=11, record_rows=True)
+  host = bsuite_b200.load_from_id(bsuite_id, batch=batch, device='cpu', seed=11, record_rows=True)
+  actions = np.random.RandomState(5).randint(cuda.num_actions, size=(steps, batch)).astype(np.int32)
+  chunk = 997                                         # fused rollouts and single steps mixed
+  for t0 in range(0, steps, chunk + 1):
+    block = torch.as_tensor(actions[t0:t0 + chunk])
+    if len(block):
+      cuda.rollout(len(block), actions=block.cuda()); host.rollout(len(block), actions=block)
+    if t0 + chunk < steps:
+      last = torch.as_tensor(actions[t0 + chunk])
+      cuda.step(last.cuda()); host.step(last)
+  got, want = cuda.logged_rows(), host.logged_rows()
+  assert list(got['columns']) == list(want['columns'])
+  counts = want['counts'].numpy()
+  np.testing.assert_array_equal(got['counts'].cpu().numpy(), counts)
+  assert counts.min() > 0
+  got_rows, want_rows = got['rows'].cpu().numpy(), want['rows'].numpy()
+  tol = 1e-6 if bsuite_id.startswith('cartpole') else 0
+  for lane in range(batch):                           # rows beyond a lane's count are unwritten memory
+    np.testing.assert_allclose(got_rows[:counts[lane], :, lane], want_rows[:counts[lane], :, lane], rtol=0, atol=tol,
+                               err_msg=f'lane {lane}')
+  cuda.close(); host.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.runs_last
+@_FIRST_GPU_RUN
+def test_device_log_rows_through_host_driven_steps_equal_the_host_path_rows():
+  """The two-phase host step (deep_sea N = 32: transitions first, rows written from its phase 1) records the same rows."""
+  import torch
+  batch, steps = 96, 1500
+  cuda = bsuite_b200.load_from_id('deep_sea/11', batch=batch, device='cuda', seed=3, record_rows=True)
+  host = bsuite_b200.load_from_id('deep_sea/11', batch=batch, device='cpu', seed=3, record_rows=True)
+  pinned = torch.as_tensor(np.random.RandomState(7).randint(2, size=(steps, batch)).astype(np.int32)).pin_memory()
+  buffers = cuda.make_host_buffers()
+  for t in range(steps):
+    cuda.step_host(pinned[t], buffers)
+    host.step(pinned[t])
+  got, want = cuda.logged_rows(), host.logged_rows()
+  counts = want['counts'].numpy()
+  np.testing.assert_array_equal(got['counts'].cpu().numpy(), counts)
+  assert counts.min() > 0
+  for lane in range(batch):
+    np.testing.assert_array_equal(got['rows'].cpu().numpy()[:counts[lane], :, lane], want['rows'].numpy()[:counts[lane], :, lane])
+  cuda.close(); host.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.runs_last
+@_FIRST_GPU_RUN
+def test_device_episode_stats_across_mid_episode_resets_equal_the_host_path():
+  """tests/test_round2_features.py pins the Logging columns across explicit mid-episode reset() calls to the reference's
+  wrapper on the host path (its CUDA variant needs the reference tree); here CUDA against that host path, after
+  every call of the same script."""
+  import torch
+  kwargs, seed, B = dict(rows=6, columns=3), 5, 4
+  make = lambda device: bsuite_b200.make('catch', batch=B, device=device, seed=seed,
+                                         engine_kwargs=dict(reward_dtype='float64', track_episodes=True), **kwargs)
+  cuda, host = make('cuda'), make('cpu')
+  rng = np.random.RandomState(0)
+  script = ['reset'] + ['step'] * 3 + ['reset'] + ['step'] * 7 + ['reset', 'reset'] + ['step'] * 11 + ['reset'] + ['step'] * 9
+  for op in script:
+    if op == 'reset':
+      got, want = cuda.reset(), host.reset()
+    else:
+      actions = torch.as_tensor(rng.randint(3, size=B).astype(np.int32))
+      got, want = cuda.step(actions.cuda()), host.step(actions)
+    np.testing.assert_array_equal(got.step_type.cpu().numpy(), want.step_type.numpy())
+    stats_cuda, stats_host = cuda.episode_stats(), host.episode_stats()
+    for key in ('steps', 'episode', 'total_return', 'episode_len', 'episode_return'):
+      np.testing.assert_array_equal(stats_cuda[key].cpu().numpy(), stats_host[key].numpy(), err_msg=f'{op} {key}')
+  cuda.close(); host.close()
