@@ -148,7 +148,20 @@ def test_load_and_record_modes(tmp_path, capsys):
 
 
 # ---------------------------------------------------------------------------- batched, device-side log rows
-_BATCHED_DEVICES = [pytest.param('cpu', id='host'), pytest.param('cuda', id='cuda', marks=pytest.mark.gpu)]
+_BATCHED_DEVICES = [pytest.param('cpu', id='host'),
+                    pytest.param('cuda', id='cuda', marks=[pytest.mark.gpu, pytest.mark.runs_last])]
+
+
+def _need_reference(device, request):
+  """The reference's source tree (build container), or -- for the CUDA variants on the GPU box, which has no tree --
+  the unmodified reference as installed under oracle/_ref.  That combination has not run anywhere yet (the container
+  has no GPU, the round's GPU budget was spent before it existed): non-strict xfail, scheduled last."""
+  if rr.reference_available():
+    return
+  if device == 'cuda' and rr.use_installed_reference():
+    request.applymarker(pytest.mark.xfail(strict=False, reason='first run on a GPU with the installed reference: reported, not gating'))
+    return
+  pytest.skip('needs the reference (source tree, or oracle/_ref for the CUDA variants)')
 
 
 def _reference_rows(env_class, kwargs, seed, lane, actions, wrapper=None, arg=None):
@@ -172,12 +185,12 @@ def _reference_rows(env_class, kwargs, seed, lane, actions, wrapper=None, arg=No
   return sink.rows
 
 
-@pytest.mark.skipif(not rr.reference_available(), reason='/root/reference only exists in the build container')
 @pytest.mark.parametrize('device', _BATCHED_DEVICES)
-def test_batched_log_rows_equal_the_reference_logging_wrapper_row_for_row(device, tmp_path):
+def test_batched_log_rows_equal_the_reference_logging_wrapper_row_for_row(device, tmp_path, request):
   """64 lanes x 1 000 episodes of catch.  Every lane's rows, recorded on the device at the
   log-spaced episode counts, equal the rows the reference wrapper writes for the same lane -- and the CSV files
   written from them load with the reference's csv_load."""
+  _need_reference(device, request)
   import torch
   B, episodes = 64, 1000
   T = episodes * 10                                 # catch: 9 transitions + the auto-reset call per episode
@@ -205,14 +218,14 @@ def test_batched_log_rows_equal_the_reference_logging_wrapper_row_for_row(device
     recording.write_lane_csvs(env, 'catch/0', str(tmp_path), lanes=range(2))
 
 
-@pytest.mark.skipif(not rr.reference_available(), reason='/root/reference only exists in the build container')
 @pytest.mark.parametrize('device', _BATCHED_DEVICES)
 @pytest.mark.parametrize('bsuite_id,env_class,kwargs,n_act,wrapper,arg', [
     ('cartpole/0', 'cartpole', {}, 3, None, None),                      # info kept in registers between steps
     ('deep_sea_stochastic/0', 'deep_sea', dict(size=10, deterministic=False, mapping_seed=42), 2, None, None),
     ('bandit_scale/3', 'bandit', dict(mapping_seed=3), 11, 'scale', 1.0),
 ])
-def test_batched_log_rows_for_other_families(device, bsuite_id, env_class, kwargs, n_act, wrapper, arg):
+def test_batched_log_rows_for_other_families(device, bsuite_id, env_class, kwargs, n_act, wrapper, arg, request):
+  _need_reference(device, request)
   import torch
   from bsuite_b200 import sweep
   B, T = 6, 3000
